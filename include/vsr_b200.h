@@ -1,0 +1,181 @@
+/*
+ * vsr_b200.h — C ABI of the B200-native explicit-state model checker for
+ * vsr-revisited/paper/VSR.tla (reference: Vanlightly/vsr-tlaplus @ 7566e8af).
+ *
+ * What this replaces.  The reference has no plugin/operator ABI: TLA+ has no FFI and the path
+ * "model-check VSR.tla under VSR.cfg" is executed by the external TLC tool
+ *     java -cp tla2tools.jar tlc2.TLC [-deadlock] [-workers N] [-fp N] [-dumpTrace tlc F] -config VSR.cfg VSR.tla
+ * so the drop-in boundary is TLC's file + CLI surface.  Each entry point below cites
+ * the part of the reference it stands in for.  Plain pointers and sizes; caller owns every buffer;
+ * no torch / C++ types.  Return codes follow TLC's exit statuses where one exists:
+ *     0 ok, 11 deadlock, 12 safety (invariant) violation, 150 spec error, 151 config error,
+ *     152 state space too large for the configured capacity, 153 system (CUDA) error, 255 other.
+ */
+#ifndef VSR_B200_H
+#define VSR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "vsr_flat.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSR_RC_OK 0
+#define VSR_RC_DEADLOCK 11
+#define VSR_RC_VIOLATION 12
+#define VSR_RC_SPEC_ERROR 150
+#define VSR_RC_CONFIG_ERROR 151
+#define VSR_RC_TOO_LARGE 152
+#define VSR_RC_SYSTEM 153
+#define VSR_RC_ERROR 255
+
+#define VSR_MAX_STATE_BYTES 256
+
+typedef struct VsrModel VsrModel; /* opaque: parsed config + selected packed layout */
+
+typedef struct VsrModelInfo {
+    int32_t replica_count, client_count, value_count;   /* VSR.cfg:4-6 */
+    int32_t start_view_on_timer_limit, restart_empty_limit; /* VSR.cfg:7-8 */
+    int32_t symmetry, view;                             /* SYMMETRY symmValues / VIEW view present (VSR.cfg:29,31) */
+    int32_t invariant;                                  /* bitmask of INVARIANT names (VSR.cfg:36-39): 1 AcknowledgedWriteNotLost
+                                                           2 AcknowledgedWritesExistOnMajority 4 NoLogDivergence 8 TestInv */
+    int32_t state_bytes;                                /* size of one packed state */
+    int32_t state_bits;                                 /* bits in use */
+    int32_t num_candidates;                             /* (action, binding) pairs tried per state */
+    int32_t spec_verified;                              /* 1 if a .tla was given and matched VSR.tla's structure */
+    uint64_t spec_hash;                                 /* FNV-1a 64 of the .tla bytes (0 if none) */
+    char value_names[VSR_MAX_V][32];                    /* model values of Values, cfg order */
+} VsrModelInfo;
+
+/* ---- loading: TLC's `-config VSR.cfg VSR.tla` (grammar of vsr-revisited/paper/VSR.cfg:1-39).
+ * tla_path may be NULL (the spec is hand-lowered; when given, it is verified to BE VSR.tla: module
+ * name :1, the 20 VARIABLES :119-138, the 19 disjuncts of Next :896-918).  On failure returns
+ * 150/151 and writes a message to err. */
+int vsr_load(const char* cfg_path, const char* tla_path, VsrModel** out, char* err, size_t errcap);
+/* same, from the text of a cfg file */
+int vsr_load_cfg_text(const char* cfg_text, const char* tla_path, VsrModel** out, char* err, size_t errcap);
+/* same, straight from constants (CONSTANTS of VSR.tla:92-96) */
+int vsr_model_create(int replica_count, int client_count, int value_count, int start_view_on_timer_limit,
+                     int restart_empty_limit, int symmetry, int view, int invariant, VsrModel** out, char* err,
+                     size_t errcap);
+void vsr_model_free(VsrModel* m);
+int vsr_model_info(const VsrModel* m, VsrModelInfo* out);
+
+/* ---- single-state operations on packed states (host; re-entrant).  A packed state is
+ * info.state_bytes bytes, 16-byte aligned. */
+int vsr_init(const VsrModel* m, void* state_out);                        /* Init, VSR.tla:323-348 */
+/* Next, VSR.tla:896-918: writes up to cap successors (state_bytes apart) in TLC's binding order,
+ * action_ids[i] = VSR_ACT_*, mult[i] = TLC bindings that successor stands for; returns the number
+ * of successors, or a negative E_* code if one cannot be represented. */
+int vsr_successors(const VsrModel* m, const void* state, void* out, size_t cap, uint8_t* action_ids, uint32_t* mult);
+int vsr_canon(const VsrModel* m, void* state);                           /* SYMMETRY representative, VSR.tla:151 */
+uint64_t vsr_fingerprint(const VsrModel* m, const void* state);          /* FP64 of the VIEW projection, VSR.tla:149-150 */
+uint32_t vsr_aux_key(const VsrModel* m, const void* state);
+int vsr_invariant(const VsrModel* m, const void* state);                 /* 0 = all hold, else mask bit of the violated one; VSR.tla:926-952 */
+int vsr_unpack(const VsrModel* m, const void* state, VsrFlatState* out);
+int vsr_pack(const VsrModel* m, const VsrFlatState* in, void* state_out);
+/* TLC value text of one state, format of state_transfer_violation_trace.txt (variables
+ * alphabetical, records in first-interned field order); returns length or -needed. */
+int vsr_state_to_tla(const VsrModel* m, const void* state, char* buf, size_t cap);
+int vsr_flat_to_tla(const VsrModel* m, const VsrFlatState* f, char* buf, size_t cap);
+const char* vsr_action_name(int action_id);
+/* "line A, col B to line C, col D of module VSR" for an action when a .tla was loaded, else "Unknown location" */
+int vsr_action_location(const VsrModel* m, int action_id, char* buf, size_t cap);
+
+/* ---- the BFS (TLC's worker loop; SURVEY §3.1, stages E1-E9) on the GPU */
+typedef struct VsrRunOpts {
+    int32_t device;              /* CUDA device ordinal */
+    int32_t check_deadlock;      /* TLC default is on; `-deadlock` turns it off.  Here default 0 (VSR has terminal states) */
+    int32_t max_depth;           /* TLC `-depth`-like bound for BFS (0 = none) */
+    int32_t stop_on_violation;   /* 1: stop at the first violating level (TLC behaviour) */
+    int32_t keep_trace;          /* 1: keep (parent, binding) per distinct state so a counterexample can be rebuilt */
+    int32_t verbose;
+    uint64_t table_capacity;     /* seen-set slots (power of two; 0 = auto from free memory) */
+    uint64_t frontier_capacity;  /* states per frontier buffer (0 = auto) */
+    uint64_t max_states;         /* stop after the level that crosses this many distinct states (0 = none) */
+    double max_seconds;          /* stop after the level that crosses this much time (0 = none) */
+    int32_t collect_levels;      /* 1: keep every level's states on the host (tests) */
+    int32_t _reserved[7];
+} VsrRunOpts;
+
+#define VSR_MAX_LEVELS 512
+typedef struct VsrStats {
+    uint64_t generated, distinct, queue;  /* TLC's "N states generated, M distinct states found, Q left on queue" */
+    int32_t depth;                        /* TLC's "depth of the complete state graph search" (Init = 1) */
+    int32_t rc;
+    int32_t complete;
+    int32_t num_levels;
+    uint64_t level_sizes[VSR_MAX_LEVELS];
+    uint64_t level_generated[VSR_MAX_LEVELS];
+    double level_ms[VSR_MAX_LEVELS];      /* device time of each level's kernels (CUDA events) */
+    uint64_t h2_ties;                     /* same-level VIEW ties with different aux variables */
+    uint64_t fp_collisions;               /* equal 64-bit fingerprints told apart by the check hash */
+    uint64_t probe_total;                 /* table slots inspected */
+    uint64_t kernel_launches;
+    double seconds_total, seconds_kernels;
+    int32_t violation_level;              /* depth of the violating state */
+    int32_t trace_len;
+    int32_t error_code;                   /* first E_* raised on the device (0 = none) */
+    int32_t _pad;
+    uint64_t violation_id;
+    uint64_t table_capacity, frontier_capacity;
+    uint64_t bytes_table, bytes_frontier;
+} VsrStats;
+
+typedef struct VsrEngine VsrEngine;
+
+/* One-call BFS on one GPU.  Fails loudly (153) when no CUDA device is usable — there is no CPU
+ * fallback.  If trace_out != NULL and a violation/deadlock is found, writes the counterexample
+ * (packed states, trace_cap capacity) with its action ids; stats.trace_len is its length. */
+int vsr_bfs(const VsrModel* m, const VsrRunOpts* opts, VsrStats* stats, void* trace_out, uint8_t* trace_actions,
+            size_t trace_cap);
+
+/* Stepwise engine (what vsr_bfs is made of; the multi-GPU host pumps these around its exchange).
+ * rank/world: this engine owns the fingerprints f with owner(f) == rank. */
+int vsr_engine_create(const VsrModel* m, const VsrRunOpts* opts, int rank, int world, VsrEngine** out, char* err,
+                      size_t errcap);
+void vsr_engine_destroy(VsrEngine* e);
+/* Set the device buffers for outgoing records (world * cap_records * record_bytes, destination-major)
+ * and a device array of `world` uint32 counters.  Caller-owned device memory. */
+int vsr_engine_record_bytes(const VsrEngine* e);
+int vsr_engine_set_send_buffers(VsrEngine* e, void* dev_records, uint64_t cap_records_per_dest, void* dev_counts);
+int vsr_engine_seed_init(VsrEngine* e);                       /* inserts Init if this rank owns it */
+/* expands the current frontier: owned successors go to the seen-set, others to the send buffers */
+int vsr_engine_expand(VsrEngine* e);
+/* inserts records received from peers (device pointer) */
+int vsr_engine_insert_records(VsrEngine* e, const void* dev_records, uint64_t n);
+/* finishes the level: resolves ties, swaps frontiers; writes this rank's level numbers */
+typedef struct VsrLevelInfo {
+    uint64_t new_states, generated, frontier_in, ties, collisions;
+    int32_t violation, deadlock, error_code, overflow;
+    uint64_t violation_id, deadlock_id;
+    double ms;
+} VsrLevelInfo;
+int vsr_engine_finish_level(VsrEngine* e, VsrLevelInfo* out);
+uint64_t vsr_engine_frontier_size(const VsrEngine* e);
+/* copies `n` states of the current frontier starting at `first` to a host buffer */
+int vsr_engine_read_frontier(VsrEngine* e, uint64_t first, uint64_t n, void* host_out);
+/* trace record of a locally owned state id: parent global id (rank << 48 | local id) and candidate index */
+int vsr_engine_trace_record(VsrEngine* e, uint64_t local_id, uint64_t* parent_out, uint32_t* cand_out);
+int vsr_engine_stats(const VsrEngine* e, VsrStats* out);
+/* Rebuild the counterexample ending at local state id (single-rank engines). */
+int vsr_engine_build_trace(VsrEngine* e, uint64_t local_id, void* trace_out, uint8_t* trace_actions, size_t trace_cap);
+
+/* Host replay helper for multi-rank traces: given a chain of candidate indices from Init, re-executes
+ * them (canonicalising as the engine does) and writes the literal states. */
+int vsr_replay_candidates(const VsrModel* m, const uint32_t* cands, int n, void* trace_out, uint8_t* trace_actions,
+                          size_t trace_cap);
+
+/* seen-set micro-benchmark: inserts n splitmix64 keys (dup_frac duplicates) into a
+ * table of `capacity` slots; returns device ms per launch in *ms_out. */
+int vsr_probe_bench(int device, uint64_t capacity, uint64_t n, double dup_frac, int iters, double* ms_out);
+
+const char* vsr_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSR_B200_H */

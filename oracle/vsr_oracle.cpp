@@ -970,7 +970,12 @@ uint32_t aux_key(const Params& p, const State& s) {
     k = k * 16u + (uint32_t)s.aux_restart;
     for (int i = 0; i < p.V; i++) {
         uint32_t code = 0;
-        if (i < (int)order.size()) code = s.acked.at(order[i].second) ? 2u : 1u;
+        if (p.symmetry) {
+            if (i < (int)order.size()) code = s.acked.at(order[i].second) ? 2u : 1u;
+        } else {
+            auto it = s.acked.find(i + 1); /* no SYMMETRY: values keep their identity, position = value index */
+            if (it != s.acked.end()) code = it->second ? 2u : 1u;
+        }
         k = k * 3u + code;
     }
     return k;
