@@ -161,6 +161,9 @@ int vsr_engine_read_frontier(VsrEngine* e, uint64_t first, uint64_t n, void* hos
 /* trace record of a locally owned state id: parent global id (rank << 48 | local id) and candidate index */
 int vsr_engine_trace_record(VsrEngine* e, uint64_t local_id, uint64_t* parent_out, uint32_t* cand_out);
 int vsr_engine_stats(const VsrEngine* e, VsrStats* out);
+const char* vsr_engine_last_error(const VsrEngine* e);
+/* with opts.collect_levels: number of states first seen at depth `level` (1-based) and, if host_out has room, a copy */
+uint64_t vsr_engine_collected(const VsrEngine* e, int level, void* host_out, uint64_t cap_states);
 /* Rebuild the counterexample ending at local state id (single-rank engines). */
 int vsr_engine_build_trace(VsrEngine* e, uint64_t local_id, void* trace_out, uint8_t* trace_actions, size_t trace_cap);
 

@@ -1,0 +1,137 @@
+"""GPU parity proper: the CUDA BFS (through the C ABI) against the CPU oracle.
+
+Bar (bit-exact, integer work): for every BFS depth the SET of canonical VIEW-projected states the GPU
+found equals the oracle's set (compared through the oracle's own canonical digest of each unpacked GPU
+state), and the four TLC scalars — states generated, distinct states, states left on queue, depth —
+are equal.  Sizes are chosen so the oracle finishes in seconds.
+"""
+import ctypes as C
+
+import pytest
+
+import orc
+
+pytestmark = pytest.mark.gpu
+
+
+def level_digest_sets(pkg, mc, res, q):
+    sb = mc.state_bytes
+    out = []
+    for raw in res.levels:
+        n = len(raw) // sb
+        flats = (pkg.checker.VsrFlatState * n)()
+        for i in range(n):
+            st = (C.c_uint8 * sb).from_buffer_copy(raw[i * sb:(i + 1) * sb])
+            rc = mc._lib.vsr_unpack(mc._h, st, C.byref(flats[i]))
+            assert rc == 0
+        digs, _ = orc.digests_of(q, flats)
+        assert len(set(digs)) == n, "GPU level holds two states with the same canonical VIEW"
+        out.append(set(digs))
+    return out
+
+
+def run_pair(pkg, R, V, L, symmetry=True, max_depth=0, inv=("AcknowledgedWriteNotLost",), table=1 << 22, frontier=1 << 20):
+    mc = pkg.ModelChecker.from_constants(R, V, L, symmetry=symmetry, invariants=inv)
+    res = mc.check(collect_levels=True, max_depth=max_depth, table_capacity=table, frontier_capacity=frontier,
+                   stop_on_violation=False)
+    inv_id = 1 if "AcknowledgedWriteNotLost" in inv else (2 if "AcknowledgedWritesExistOnMajority" in inv else 4)
+    q = orc.params(R, V, L, symmetry=symmetry and V > 1, invariant=inv_id)
+    o = orc.bfs(q, workers=8, max_depth=max_depth, keep_trace=False, digests=True)
+    return mc, res, q, o
+
+
+def assert_same_exploration(pkg, mc, res, q, o, complete):
+    assert res.error_code == 0
+    assert sum(o.assumptions[:5]) + sum(o.assumptions[6:]) == 0, "oracle audit of the slot-encoding assumptions failed"
+    assert res.level_sizes == o.level_sizes
+    # successors generated while expanding each depth (the last depth reached is not expanded under -depth)
+    ng = len(o.level_generated)
+    assert res.level_generated[:ng] == o.level_generated
+    gpu_sets = level_digest_sets(pkg, mc, res, q)
+    assert len(gpu_sets) == len(o.level_digests)
+    for d, (g, w) in enumerate(zip(gpu_sets, o.level_digests)):
+        assert g == set(w), f"depth {d + 1}: GPU and oracle state sets differ"
+    assert res.distinct == o.distinct
+    assert res.generated == o.generated
+    assert res.depth == o.depth
+    assert res.h2_ties == o.h2_ties
+    if complete:
+        assert res.complete and o.complete and res.queue == 0 == o.queue
+
+
+@pytest.mark.parametrize("R,V,L,sym", [(2, 1, 1, True), (2, 2, 2, True), (2, 2, 2, False), (3, 1, 1, True)])
+def test_full_state_space_matches_oracle(pkg, R, V, L, sym):
+    mc, res, q, o = run_pair(pkg, R, V, L, symmetry=sym)
+    assert res.rc == 0
+    assert_same_exploration(pkg, mc, res, q, o, complete=True)
+
+
+def test_cfg1_scalars(pkg):
+    """BASELINE configs[0]: ReplicaCount=2 Values={v1} StartViewOnTimerLimit=1, full BFS (deadlock checking off)."""
+    mc = pkg.ModelChecker.from_constants(2, 1, 1)
+    res = mc.check()
+    assert (res.generated, res.distinct, res.queue, res.depth, res.rc, res.complete) == (100, 76, 0, 14, 0, True)
+
+
+@pytest.mark.parametrize("R,V,L,depth", [(3, 2, 2, 11), (3, 3, 3, 10), (5, 2, 2, 7), (3, 2, 1, 14), (4, 2, 2, 8), (3, 3, 2, 10)])
+def test_bounded_depth_matches_oracle(pkg, R, V, L, depth):
+    """cfg2 (shipped VSR.cfg), cfg3 (README), cfg4 (R=5) and friends, as deep as the oracle goes in seconds."""
+    mc, res, q, o = run_pair(pkg, R, V, L, max_depth=depth)
+    assert_same_exploration(pkg, mc, res, q, o, complete=False)
+    assert res.queue == res.level_sizes[-1]
+
+
+def test_no_symmetry_no_view_matches_oracle(pkg):
+    mc = pkg.ModelChecker.from_cfg_text(pkg.cfg_text(3, ["a", "b"], 2, view=False, symmetry=False))
+    res = mc.check(collect_levels=True, max_depth=9, table_capacity=1 << 22, frontier_capacity=1 << 20)
+    q = orc.params(3, 2, 2, symmetry=False, view=False)
+    o = orc.bfs(q, workers=8, max_depth=9, keep_trace=False, digests=True)
+    assert_same_exploration(pkg, mc, res, q, o, complete=False)
+
+
+def test_deterministic_across_runs(pkg):
+    mc = pkg.ModelChecker.from_constants(3, 2, 2)
+    a = mc.check(collect_levels=True, max_depth=10, table_capacity=1 << 21, frontier_capacity=1 << 19)
+    b = mc.check(collect_levels=True, max_depth=10, table_capacity=1 << 23, frontier_capacity=1 << 19)
+    sb = mc.state_bytes
+    for la, lb in zip(a.levels, b.levels):
+        sa = {la[i:i + sb] for i in range(0, len(la), sb)}
+        sbb = {lb[i:i + sb] for i in range(0, len(lb), sb)}
+        assert sa == sbb
+    assert (a.generated, a.distinct, a.depth) == (b.generated, b.distinct, b.depth)
+
+
+def test_counterexample_is_a_behaviour(pkg):
+    """AcknowledgedWritesExistOnMajority is violated early; the GPU's counterexample must be a literal behaviour
+    of the spec (every step in the oracle's Next, last state violating), of minimal length (BFS)."""
+    inv = ("AcknowledgedWritesExistOnMajority",)
+    mc = pkg.ModelChecker.from_constants(3, 2, 2, invariants=inv)
+    res = mc.check(table_capacity=1 << 22, frontier_capacity=1 << 20)
+    q = orc.params(3, 2, 2, invariant=2)
+    o = orc.bfs(q, workers=8, keep_trace=False)
+    if o.rc != 12:
+        pytest.skip("invariant not violated in this configuration")
+    assert res.rc == 12
+    assert res.violation_level == o.depth
+    assert len(res.trace) == o.depth
+    assert res.trace[0][0] == "Initial predicate"
+    L = orc.lib()
+    flats = [mc.unpack(st) for _, st in res.trace]
+    for i in range(len(flats) - 1):
+        cap = 256
+        succ = (pkg.checker.VsrFlatState * cap)()
+        acts = (C.c_int * cap)()
+        n = L.orc_successors_flat(q, C.byref(flats[i]), succ, acts, cap)
+        want = orc.digests_full_of(orc.params(3, 2, 2, symmetry=False, invariant=2), (pkg.checker.VsrFlatState * 1)(flats[i + 1]))[0]
+        got = orc.digests_full_of(orc.params(3, 2, 2, symmetry=False, invariant=2), succ)[:n]
+        names = [pkg.ACTION_NAMES[acts[k]] for k in range(n)]
+        assert any(g == want and nm == res.trace[i + 1][0] for g, nm in zip(got, names)), f"step {i + 1} is not a step of Next"
+    assert L.orc_invariant_flat(q, C.byref(flats[-1])) == 0
+    for f in flats[:-1]:
+        assert L.orc_invariant_flat(q, C.byref(f)) == 1
+
+
+def test_frontier_overflow_is_loud(pkg):
+    mc = pkg.ModelChecker.from_constants(3, 2, 2)
+    res = mc.check(max_depth=12, table_capacity=1 << 20, frontier_capacity=256)
+    assert res.rc == 152

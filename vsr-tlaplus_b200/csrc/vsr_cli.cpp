@@ -1,0 +1,114 @@
+/*
+ * vsr_cli.cpp — `vsrmc`: TLC's command line for the one path this repo replaces,
+ *     java -cp tla2tools.jar tlc2.TLC [-deadlock] [-depth N] [-fp N] [-dumpTrace tlc FILE] -config VSR.cfg VSR.tla
+ * becomes
+ *     vsrmc [-deadlock] [-depth N] [-fp 0] [-dumpTrace tlc FILE] [-gpu N] -config VSR.cfg [VSR.tla]
+ * with TLC's summary lines and exit statuses (0, 11 deadlock, 12 invariant, 150/151 parse errors).
+ * Thin: all work is behind the C ABI (include/vsr_b200.h).
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/vsr_b200.h"
+
+static void usage() {
+    fprintf(stderr,
+            "usage: vsrmc -config FILE.cfg [SPEC.tla] [options]\n"
+            "  -deadlock            do NOT check for deadlock (TLC's flag; TLC checks by default, and so does vsrmc)\n"
+            "  -depth N             stop after BFS depth N\n"
+            "  -dumpTrace tlc FILE  write a counterexample in TLC's `dumpTrace tlc` format\n"
+            "  -fp N                fingerprint polynomial index; only 0 (TLC's Polys[0]) is available\n"
+            "  -workers N           accepted for compatibility; the BFS runs on the GPU\n"
+            "  -gpu N               CUDA device ordinal (default 0)\n"
+            "  -table N / -frontier N   seen-set slots / states per frontier buffer (default: from free memory)\n"
+            "  -continue            keep exploring after the first violation\n"
+            "  -notrace             do not keep parent records (no counterexample)\n");
+}
+
+int main(int argc, char** argv) {
+    const char *cfg = nullptr, *tla = nullptr, *dump = nullptr;
+    VsrRunOpts o;
+    memset(&o, 0, sizeof o);
+    o.check_deadlock = 1; /* TLC's default */
+    o.stop_on_violation = 1;
+    o.keep_trace = 1;
+    o.verbose = 1;
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i];
+        if (a == "-config" && i + 1 < argc) cfg = argv[++i];
+        else if (a == "-deadlock") o.check_deadlock = 0;
+        else if (a == "-depth" && i + 1 < argc) o.max_depth = atoi(argv[++i]);
+        else if (a == "-dumpTrace" && i + 2 < argc) {
+            if (strcmp(argv[i + 1], "tlc") != 0) { fprintf(stderr, "Error: only `-dumpTrace tlc FILE` is supported\n"); return 255; }
+            dump = argv[i + 2];
+            i += 2;
+        } else if (a == "-fp" && i + 1 < argc) {
+            if (atoi(argv[++i]) != 0) { fprintf(stderr, "Error: only -fp 0 is available\n"); return 255; }
+        } else if (a == "-workers" && i + 1 < argc) i++;
+        else if (a == "-gpu" && i + 1 < argc) o.device = atoi(argv[++i]);
+        else if (a == "-table" && i + 1 < argc) o.table_capacity = strtoull(argv[++i], 0, 10);
+        else if (a == "-frontier" && i + 1 < argc) o.frontier_capacity = strtoull(argv[++i], 0, 10);
+        else if (a == "-continue") o.stop_on_violation = 0;
+        else if (a == "-notrace") o.keep_trace = 0;
+        else if (a == "-h" || a == "-help" || a == "--help") { usage(); return 0; }
+        else if (a[0] != '-') tla = argv[i];
+        else { fprintf(stderr, "Error: unrecognized option %s\n", a.c_str()); usage(); return 255; }
+    }
+    if (!cfg) { usage(); return 255; }
+    char err[1024];
+    VsrModel* m = nullptr;
+    int rc = vsr_load(cfg, tla, &m, err, sizeof err);
+    if (rc) { fprintf(stderr, "Error: %s\n", err); return rc; }
+    VsrModelInfo info;
+    vsr_model_info(m, &info);
+    printf("%s\n", vsr_version());
+    printf("Model: ReplicaCount=%d ClientCount=%d |Values|=%d StartViewOnTimerLimit=%d RestartEmptyLimit=%d%s%s; packed state %d bytes (%d bits), %d candidate bindings per state\n",
+           info.replica_count, info.client_count, info.value_count, info.start_view_on_timer_limit, info.restart_empty_limit,
+           info.view ? " VIEW view" : "", info.symmetry ? " SYMMETRY symmValues" : "", info.state_bytes, info.state_bits, info.num_candidates);
+    if (tla) printf("Spec %s verified as MODULE VSR (hash %016llx)\n", tla, (unsigned long long)info.spec_hash);
+    printf("Running breadth-first search Model-Checking with fp 0 on GPU %d.\n", o.device);
+    VsrStats st;
+    const size_t tcap = 512;
+    std::vector<unsigned char> trace(tcap * (size_t)info.state_bytes);
+    std::vector<uint8_t> acts(tcap);
+    rc = vsr_bfs(m, &o, &st, trace.data(), acts.data(), tcap);
+    if (rc == VSR_RC_VIOLATION || rc == VSR_RC_DEADLOCK) {
+        if (rc == VSR_RC_VIOLATION) printf("Error: Invariant %s is violated.\n", (info.invariant & 1) ? "AcknowledgedWriteNotLost" : "AcknowledgedWritesExistOnMajority");
+        else printf("Error: Deadlock reached.\n");
+        printf("Error: The behavior up to this point is:\n");
+        std::vector<char> buf(1 << 18);
+        std::string dumptext = "<<\n";
+        for (int i = 0; i < st.trace_len; i++) {
+            const unsigned char* s = trace.data() + (size_t)i * info.state_bytes;
+            char loc[128];
+            vsr_action_location(m, acts[i], loc, sizeof loc);
+            vsr_state_to_tla(m, s, buf.data(), buf.size());
+            if (i == 0) printf("State 1: <Initial predicate>\n%s\n", buf.data());
+            else printf("State %d: <%s %s>\n%s\n", i + 1, vsr_action_name(acts[i]), loc, buf.data());
+            dumptext += "[\n _TEAction |-> [\n   position |-> " + std::to_string(i + 1) + ",\n   name |-> \"" + vsr_action_name(acts[i]) +
+                        "\",\n   location |-> \"" + loc + "\"\n ],\n" + buf.data() + "]" + (i + 1 < st.trace_len ? ",\n" : "\n");
+        }
+        dumptext += ">>";
+        if (dump) {
+            FILE* f = fopen(dump, "w");
+            if (f) { fputs(dumptext.c_str(), f); fclose(f); printf("Trace written to %s\n", dump); }
+        }
+    } else if (rc) {
+        fprintf(stderr, "Error: run failed with status %d (device error code %d)\n", rc, st.error_code);
+    } else if (st.complete) {
+        printf("Model checking completed. No error has been found.\n");
+    }
+    printf("%llu states generated, %llu distinct states found, %llu states left on queue.\n", (unsigned long long)st.generated,
+           (unsigned long long)st.distinct, (unsigned long long)st.queue);
+    if (st.complete) printf("The depth of the complete state graph search is %d.\n", st.depth);
+    else printf("The depth of the state graph search so far is %d.\n", st.depth);
+    printf("Finished in %.3f s (kernels %.3f s): %.0f distinct states/s; same-level VIEW ties %llu, fingerprint collisions detected %llu\n",
+           st.seconds_total, st.seconds_kernels, st.distinct / (st.seconds_total > 0 ? st.seconds_total : 1), (unsigned long long)st.h2_ties,
+           (unsigned long long)st.fp_collisions);
+    vsr_model_free(m);
+    return rc;
+}

@@ -1,0 +1,490 @@
+/*
+ * vsr_gpu.cu — host driver of the BFS wavefront and the GPU half of the C ABI
+ * (vsr_bfs, vsr_engine_*; include/vsr_b200.h).  "Thin C++ driver that pumps wavefronts":
+ * per level one expand launch (plus insert launches for records received from peer ranks),
+ * one small counter read-back, swap frontiers.  Kernels: vsr_gpu.cuh.
+ * There is NO CPU fallback: without a usable CUDA device every entry point returns 153.
+ */
+#include <stdio.h>
+#include <string.h>
+
+#include <chrono>
+#include <string>
+#include <vector>
+
+#include "vsr_gpu.cuh"
+#include "vsr_model.h"
+
+namespace vsr {
+
+struct GpuOps {
+    int R, V, K, nw, bytes, rec_bytes;
+    size_t expand_smem;
+    cudaError_t (*launch_expand)(const ExpandParams&, int grid, cudaStream_t);
+    cudaError_t (*launch_insert)(const InsertParams&, cudaStream_t);
+    cudaError_t (*prepare)(int* blocks_per_sm);
+};
+
+template <class L> struct GpuThunks {
+    static cudaError_t prepare(int* blocks_per_sm) {
+        cudaError_t e = cudaFuncSetAttribute(expand_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlockSmem<L>));
+        if (e != cudaSuccess) return e;
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, expand_kernel<L>, EXP_WARPS * 32, sizeof(BlockSmem<L>));
+    }
+    static cudaError_t launch_expand(const ExpandParams& p, int grid, cudaStream_t st) {
+        expand_kernel<L><<<grid, EXP_WARPS * 32, sizeof(BlockSmem<L>), st>>>(p);
+        return cudaGetLastError();
+    }
+    static cudaError_t launch_insert(const InsertParams& q, cudaStream_t st) {
+        if (q.n == 0) return cudaSuccess;
+        const unsigned blocks = (unsigned)((q.n + 255) / 256);
+        insert_kernel<L><<<blocks, 256, 0, st>>>(q);
+        return cudaGetLastError();
+    }
+    static const GpuOps* get() {
+        static const GpuOps ops = {L::R, L::V, L::K, L::NW, L::BYTES, (int)(L::BYTES + sizeof(RecHdr)), sizeof(BlockSmem<L>),
+                                   launch_expand, launch_insert, prepare};
+        return &ops;
+    }
+};
+
+const GpuOps* find_gpu_ops(int R, int V, int K) {
+#define X(r, v, k) \
+    if (R == r && V == v && K == k) return GpuThunks<Layout<r, v, k>>::get();
+    VSR_FOR_EACH_CONFIG(X)
+#undef X
+    return nullptr;
+}
+
+} // namespace vsr
+
+using namespace vsr;
+
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t _e = (call);                                                                        \
+        if (_e != cudaSuccess) {                                                                        \
+            snprintf(e->last_error, sizeof e->last_error, "%s failed: %s", #call, cudaGetErrorString(_e)); \
+            return VSR_RC_SYSTEM;                                                                       \
+        }                                                                                               \
+    } while (0)
+
+struct VsrEngine {
+    const VsrModel* m = nullptr;
+    const GpuOps* g = nullptr;
+    VsrRunOpts opts;
+    int rank = 0, world = 1, owner_shift = 64;
+    int device = 0, sms = 0, blocks_per_sm = 1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    /* device memory */
+    uint64_t* table = nullptr;
+    uint64_t table_cap = 0;
+    uint32_t* frontier[2] = {nullptr, nullptr};
+    uint64_t frontier_cap = 0;
+    uint64_t* trace = nullptr;
+    uint64_t trace_cap = 0;
+    DevCounters* ctr = nullptr;
+    TieRec* ties = nullptr;
+    uint64_t tie_cap = 0;
+    uint64_t* fp_tab = nullptr;
+    uint8_t* send = nullptr;
+    uint64_t send_cap = 0;
+    unsigned int* send_count = nullptr;
+    uint8_t* init_rec = nullptr;
+    /* BFS position */
+    int cur = 0;                 /* which frontier buffer is the current level */
+    uint64_t n_cur = 0;          /* states in it */
+    uint64_t cur_base = 0;       /* local id of its first state */
+    uint64_t next_base = 0;      /* local id the next level starts at */
+    int level = 0;               /* depth of the current frontier (Init = 1) */
+    bool level_open = false;     /* counters reset for the level being generated */
+    VsrStats st;
+    double level_ms_acc = 0;
+    std::vector<std::vector<uint8_t>> collected; /* per level states (collect_levels) */
+    char last_error[256] = {0};
+};
+
+static int engine_reset_level(VsrEngine* e) {
+    CK(cudaMemsetAsync(e->ctr, 0, sizeof(DevCounters), e->stream));
+    static const unsigned long long ones = ~0ull;
+    CK(cudaMemcpyAsync(&e->ctr->viol_id, &ones, 8, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(&e->ctr->dead_id, &ones, 8, cudaMemcpyHostToDevice, e->stream));
+    if (e->send_count) CK(cudaMemsetAsync(e->send_count, 0, sizeof(unsigned int) * e->world, e->stream));
+    e->level_open = true;
+    e->level_ms_acc = 0;
+    return 0;
+}
+
+static void fill_params(VsrEngine* e, ExpandParams& p) {
+    memset(&p, 0, sizeof p);
+    p.in = e->frontier[e->cur];
+    p.n_in = e->n_cur;
+    p.in_base = e->cur_base;
+    p.out = e->frontier[e->cur ^ 1];
+    p.out_cap = e->frontier_cap;
+    p.out_base = e->next_base;
+    p.table = e->table;
+    p.table_mask = e->table_cap - 1;
+    p.trace = e->trace;
+    p.trace_cap = e->trace_cap;
+    p.ctr = e->ctr;
+    p.ties = e->ties;
+    p.tie_cap = e->tie_cap;
+    p.fp_tab = e->fp_tab;
+    p.run = e->m->run;
+    p.level = e->level + 1;
+    p.check_deadlock = e->opts.check_deadlock;
+    p.rank = e->rank;
+    p.world = e->world;
+    p.owner_shift = e->owner_shift;
+    p.send = e->send;
+    p.send_cap = e->send_cap;
+    p.send_count = e->send_count;
+}
+
+extern "C" {
+
+int vsr_engine_create(const VsrModel* m, const VsrRunOpts* opts, int rank, int world, VsrEngine** out, char* err, size_t errcap) {
+    auto fail = [&](int rc, const std::string& msg) {
+        if (err && errcap) snprintf(err, errcap, "%s", msg.c_str());
+        return rc;
+    };
+    if (!m || !opts || !out) return fail(VSR_RC_ERROR, "null argument");
+    if (!m->gpu) return fail(VSR_RC_CONFIG_ERROR, "no GPU kernels compiled for this configuration");
+    if (world < 1 || (world & (world - 1)) || rank < 0 || rank >= world) return fail(VSR_RC_CONFIG_ERROR, "world must be a power of two and 0 <= rank < world");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(VSR_RC_SYSTEM, std::string("no usable CUDA device (") + cudaGetErrorString(ce) + "): the BFS runs on the GPU only, there is no CPU fallback");
+    VsrEngine* e = new VsrEngine();
+    e->m = m;
+    e->g = m->gpu;
+    e->opts = *opts;
+    e->rank = rank;
+    e->world = world;
+    int lg = 0;
+    while ((1 << lg) < world) lg++;
+    e->owner_shift = world > 1 ? 64 - lg : 64;
+    e->device = opts->device;
+    memset(&e->st, 0, sizeof e->st);
+    auto bail = [&](const char* what, cudaError_t c) {
+        std::string msg = std::string(what) + ": " + cudaGetErrorString(c);
+        vsr_engine_destroy(e);
+        return fail(VSR_RC_SYSTEM, msg);
+    };
+    if ((ce = cudaSetDevice(e->device)) != cudaSuccess) return bail("cudaSetDevice", ce);
+    cudaDeviceProp prop;
+    if ((ce = cudaGetDeviceProperties(&prop, e->device)) != cudaSuccess) return bail("cudaGetDeviceProperties", ce);
+    e->sms = prop.multiProcessorCount;
+    if ((ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", ce);
+    cudaEventCreate(&e->ev0);
+    cudaEventCreate(&e->ev1);
+    if ((ce = e->g->prepare(&e->blocks_per_sm)) != cudaSuccess) return bail("kernel attributes", ce);
+    if (e->blocks_per_sm < 1) e->blocks_per_sm = 1;
+    /* capacities */
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    uint64_t tcap = opts->table_capacity, fcap = opts->frontier_capacity;
+    const uint64_t S = (uint64_t)e->g->bytes;
+    if (!tcap) { /* table 16 B/slot + trace 8 B per state at load <= 1/2  ->  20 B per slot; give it ~45% of free memory */
+        tcap = 1;
+        while (tcap * 2 * 20 <= (uint64_t)(free_b * 0.45)) tcap *= 2;
+    }
+    if (tcap & (tcap - 1)) { uint64_t p2 = 1; while (p2 < tcap) p2 *= 2; tcap = p2; }
+    if (!fcap) fcap = (uint64_t)(free_b * 0.40) / (2 * S);
+    if (fcap < 64) fcap = 64;
+    e->table_cap = tcap;
+    e->frontier_cap = fcap;
+    e->trace_cap = opts->keep_trace ? tcap / 2 + 64 : 0;
+    e->tie_cap = 1 << 16;
+    if ((ce = cudaMalloc(&e->table, tcap * 16)) != cudaSuccess) return bail("cudaMalloc(seen-set)", ce);
+    if ((ce = cudaMemsetAsync(e->table, 0, tcap * 16, e->stream)) != cudaSuccess) return bail("memset", ce);
+    for (int i = 0; i < 2; i++)
+        if ((ce = cudaMalloc(&e->frontier[i], fcap * S)) != cudaSuccess) return bail("cudaMalloc(frontier)", ce);
+    if (e->trace_cap && (ce = cudaMalloc(&e->trace, e->trace_cap * 8)) != cudaSuccess) return bail("cudaMalloc(trace)", ce);
+    if ((ce = cudaMalloc(&e->ctr, sizeof(DevCounters))) != cudaSuccess) return bail("cudaMalloc", ce);
+    if ((ce = cudaMalloc(&e->ties, e->tie_cap * sizeof(TieRec))) != cudaSuccess) return bail("cudaMalloc", ce);
+    if ((ce = cudaMalloc(&e->fp_tab, 256 * 8)) != cudaSuccess) return bail("cudaMalloc", ce);
+    if ((ce = cudaMalloc(&e->init_rec, e->g->rec_bytes)) != cudaSuccess) return bail("cudaMalloc", ce);
+    if ((ce = cudaMemcpyAsync(e->fp_tab, fp64_table(), 256 * 8, cudaMemcpyHostToDevice, e->stream)) != cudaSuccess) return bail("memcpy", ce);
+    e->st.table_capacity = tcap;
+    e->st.frontier_capacity = fcap;
+    e->st.bytes_table = tcap * 16;
+    e->st.bytes_frontier = 2 * fcap * S;
+    if ((ce = cudaStreamSynchronize(e->stream)) != cudaSuccess) return bail("sync", ce);
+    *out = e;
+    return 0;
+}
+
+void vsr_engine_destroy(VsrEngine* e) {
+    if (!e) return;
+    cudaFree(e->table);
+    cudaFree(e->frontier[0]);
+    cudaFree(e->frontier[1]);
+    cudaFree(e->trace);
+    cudaFree(e->ctr);
+    cudaFree(e->ties);
+    cudaFree(e->fp_tab);
+    cudaFree(e->init_rec);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int vsr_engine_record_bytes(const VsrEngine* e) { return e->g->rec_bytes; }
+
+int vsr_engine_set_send_buffers(VsrEngine* e, void* dev_records, uint64_t cap_records_per_dest, void* dev_counts) {
+    e->send = (uint8_t*)dev_records;
+    e->send_cap = cap_records_per_dest;
+    e->send_count = (unsigned int*)dev_counts;
+    return 0;
+}
+
+/* Level 1: the single initial state (VSR.tla:323-348), inserted by the rank that owns its fingerprint.
+   The "current frontier" is empty and the "next" frontier receives Init; finish_level() then advances. */
+int vsr_engine_seed_init(VsrEngine* e) {
+    const ModelOps* ops = e->m->ops;
+    std::vector<uint8_t> rec(e->g->rec_bytes, 0);
+    ops->init((uint32_t*)rec.data());
+    uint64_t fp = ops->fingerprint((const uint32_t*)rec.data(), e->m->run.use_view);
+    if (fp == 0) fp = 1;
+    const int owner = e->world > 1 ? (int)(fp >> e->owner_shift) : e->rank;
+    e->level = 0;
+    e->n_cur = 0;
+    e->cur_base = 0;
+    e->next_base = 0;
+    int rc = engine_reset_level(e);
+    if (rc) return rc;
+    if (owner != e->rank) return 0;
+    RecHdr* h = (RecHdr*)(rec.data() + e->g->bytes);
+    h->fp = fp;
+    h->meta = 0; /* 0 = "compute on device" (insert_kernel) */
+    h->parent = ~0ull >> 12;
+    h->cand = 0;
+    h->mult = 1;
+    CK(cudaMemcpyAsync(e->init_rec, rec.data(), rec.size(), cudaMemcpyHostToDevice, e->stream));
+    InsertParams q;
+    fill_params(e, q.e);
+    q.e.level = 1;
+    q.recs = e->init_rec;
+    q.n = 1;
+    CK(e->g->launch_insert(q, e->stream));
+    e->st.kernel_launches++;
+    return 0;
+}
+
+int vsr_engine_expand(VsrEngine* e) {
+    if (!e->level_open) {
+        int rc = engine_reset_level(e);
+        if (rc) return rc;
+    }
+    if (e->n_cur == 0) return 0;
+    ExpandParams p;
+    fill_params(e, p);
+    const uint64_t chunks = (e->n_cur + 31) / 32;
+    uint64_t want_blocks = (chunks + EXP_WARPS - 1) / EXP_WARPS;
+    const uint64_t max_blocks = (uint64_t)e->sms * e->blocks_per_sm; /* persistent: whole multiples of the SM count */
+    int grid = (int)(want_blocks < max_blocks ? want_blocks : max_blocks);
+    if (grid < 1) grid = 1;
+    CK(cudaEventRecord(e->ev0, e->stream));
+    CK(e->g->launch_expand(p, grid, e->stream));
+    CK(cudaEventRecord(e->ev1, e->stream));
+    e->st.kernel_launches++;
+    CK(cudaEventSynchronize(e->ev1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+    e->level_ms_acc += ms;
+    return 0;
+}
+
+int vsr_engine_insert_records(VsrEngine* e, const void* dev_records, uint64_t n) {
+    if (!e->level_open) {
+        int rc = engine_reset_level(e);
+        if (rc) return rc;
+    }
+    if (n == 0) return 0;
+    InsertParams q;
+    fill_params(e, q.e);
+    q.recs = (const uint8_t*)dev_records;
+    q.n = n;
+    CK(cudaEventRecord(e->ev0, e->stream));
+    CK(e->g->launch_insert(q, e->stream));
+    CK(cudaEventRecord(e->ev1, e->stream));
+    e->st.kernel_launches++;
+    CK(cudaEventSynchronize(e->ev1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+    e->level_ms_acc += ms;
+    return 0;
+}
+
+int vsr_engine_finish_level(VsrEngine* e, VsrLevelInfo* out) {
+    DevCounters c;
+    CK(cudaMemcpyAsync(&c, e->ctr, sizeof c, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    VsrLevelInfo li;
+    memset(&li, 0, sizeof li);
+    li.new_states = c.out_count;
+    li.generated = c.generated;
+    li.frontier_in = e->n_cur;
+    li.ties = c.ties;
+    li.collisions = c.collisions;
+    li.violation = c.viol_id != ~0ull;
+    li.violation_id = c.viol_id;
+    li.deadlock = c.dead_id != ~0ull;
+    li.deadlock_id = c.dead_id;
+    li.error_code = c.error;
+    li.overflow = c.overflow;
+    li.ms = e->level_ms_acc;
+    if (c.overflow) {
+        snprintf(e->last_error, sizeof e->last_error, "capacity exceeded (%s): %llu new states this level, frontier capacity %llu",
+                 c.overflow == 1 ? "frontier" : (c.overflow == 2 ? "tie list" : "send buffer"), (unsigned long long)c.out_count,
+                 (unsigned long long)e->frontier_cap);
+    }
+    /* advance */
+    const uint64_t n_new = c.out_count <= e->frontier_cap ? c.out_count : e->frontier_cap;
+    e->st.generated += c.generated;
+    e->st.distinct += n_new;
+    e->st.h2_ties += c.ties;
+    e->st.fp_collisions += c.collisions;
+    e->st.probe_total += c.probes;
+    e->st.seconds_kernels += e->level_ms_acc * 1e-3;
+    if (c.error && !e->st.error_code) e->st.error_code = c.error;
+    const int gen_level = e->level + 1; /* depth of the states just generated */
+    if (e->level >= 1 && e->level - 1 < VSR_MAX_LEVELS) {
+        e->st.level_generated[e->level - 1] = c.generated;
+        e->st.level_ms[e->level - 1] = e->level_ms_acc;
+    }
+    if (n_new > 0 && gen_level - 1 < VSR_MAX_LEVELS) {
+        e->st.level_sizes[gen_level - 1] = n_new;
+        e->st.num_levels = gen_level;
+    }
+    if (li.violation && e->st.violation_level == 0) {
+        e->st.violation_level = gen_level;
+        e->st.violation_id = c.viol_id;
+    }
+    e->cur ^= 1;
+    e->cur_base = e->next_base;
+    e->n_cur = n_new;
+    e->next_base += n_new;
+    e->level = gen_level;
+    e->level_open = false;
+    if (e->opts.collect_levels && n_new) {
+        std::vector<uint8_t> host((size_t)n_new * e->g->bytes);
+        CK(cudaMemcpy(host.data(), e->frontier[e->cur], host.size(), cudaMemcpyDeviceToHost));
+        e->collected.push_back(std::move(host));
+    }
+    if (out) *out = li;
+    return 0;
+}
+
+uint64_t vsr_engine_frontier_size(const VsrEngine* e) { return e->n_cur; }
+
+int vsr_engine_read_frontier(VsrEngine* e, uint64_t first, uint64_t n, void* host_out) {
+    if (first + n > e->n_cur) return VSR_RC_ERROR;
+    CK(cudaMemcpy(host_out, (const uint8_t*)e->frontier[e->cur] + first * e->g->bytes, n * e->g->bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int vsr_engine_trace_record(VsrEngine* e, uint64_t local_id, uint64_t* parent_out, uint32_t* cand_out) {
+    if (!e->trace || local_id >= e->trace_cap) return VSR_RC_ERROR;
+    uint64_t t = 0;
+    CK(cudaMemcpy(&t, e->trace + local_id, 8, cudaMemcpyDeviceToHost));
+    *parent_out = t >> 12;
+    *cand_out = (uint32_t)(t & 0xFFF);
+    return 0;
+}
+
+int vsr_engine_stats(const VsrEngine* e, VsrStats* out) {
+    *out = e->st;
+    return 0;
+}
+
+const char* vsr_engine_last_error(const VsrEngine* e) { return e->last_error; }
+
+/* number of states collected for `level` (1-based) and a copy of them (tests) */
+uint64_t vsr_engine_collected(const VsrEngine* e, int level, void* host_out, uint64_t cap_states) {
+    if (level < 1 || (size_t)level > e->collected.size()) return 0;
+    const std::vector<uint8_t>& v = e->collected[level - 1];
+    const uint64_t n = v.size() / e->g->bytes;
+    if (host_out && cap_states >= n) memcpy(host_out, v.data(), v.size());
+    return n;
+}
+
+int vsr_engine_build_trace(VsrEngine* e, uint64_t local_id, void* trace_out, uint8_t* trace_actions, size_t trace_cap) {
+    if (e->world != 1) return -VSR_RC_ERROR; /* multi-rank chains are walked by the host that owns the collectives */
+    std::vector<uint32_t> cands;
+    uint64_t id = local_id;
+    const uint64_t root_parent = (~0ull >> 12) & ((1ull << 52) - 1);
+    for (int guard = 0; guard < 100000; guard++) {
+        uint64_t parent;
+        uint32_t cand;
+        if (vsr_engine_trace_record(e, id, &parent, &cand)) return -VSR_RC_ERROR;
+        if (parent == root_parent) break; /* Init */
+        cands.push_back(cand);
+        id = parent & ((1ull << 40) - 1);
+    }
+    std::vector<uint32_t> fwd(cands.rbegin(), cands.rend());
+    return vsr_replay_candidates(e->m, fwd.data(), (int)fwd.size(), trace_out, trace_actions, trace_cap);
+}
+
+int vsr_bfs(const VsrModel* m, const VsrRunOpts* opts, VsrStats* stats, void* trace_out, uint8_t* trace_actions, size_t trace_cap) {
+    if (!m || !opts || !stats) return VSR_RC_ERROR;
+    const double t0 = now_s();
+    VsrEngine* e = nullptr;
+    char err[256];
+    int rc = vsr_engine_create(m, opts, 0, 1, &e, err, sizeof err);
+    if (rc) {
+        memset(stats, 0, sizeof *stats);
+        stats->rc = rc;
+        if (opts->verbose) fprintf(stderr, "vsr_bfs: %s\n", err);
+        return rc;
+    }
+    rc = vsr_engine_seed_init(e);
+    VsrLevelInfo li;
+    if (!rc) rc = vsr_engine_finish_level(e, &li);
+    int result = 0;
+    bool complete = false;
+    uint64_t bad_id = ~0ull;
+    while (!rc) {
+        if (li.error_code) { result = VSR_RC_ERROR; break; }
+        if (li.overflow) { result = VSR_RC_TOO_LARGE; break; }
+        if (li.violation && opts->stop_on_violation) { result = VSR_RC_VIOLATION; bad_id = li.violation_id; break; }
+        if (li.violation && !result) { result = VSR_RC_VIOLATION; bad_id = li.violation_id; }
+        if (li.deadlock) { result = VSR_RC_DEADLOCK; bad_id = li.deadlock_id; break; }
+        if (e->n_cur == 0) { complete = true; break; }
+        if (opts->max_depth && e->level >= opts->max_depth) break;
+        if (opts->max_states && e->st.distinct >= opts->max_states) break;
+        if (opts->max_seconds > 0 && now_s() - t0 >= opts->max_seconds) break;
+        if (e->level >= 254) { result = VSR_RC_TOO_LARGE; break; } /* 8-bit level tag in the seen-set */
+        rc = vsr_engine_expand(e);
+        if (rc) break;
+        rc = vsr_engine_finish_level(e, &li);
+        if (opts->verbose && !rc)
+            fprintf(stderr, "depth %3d: %12llu new  %12llu generated  %8.3f ms\n", e->level, (unsigned long long)li.new_states,
+                    (unsigned long long)li.generated, li.ms);
+    }
+    if (rc) result = rc;
+    VsrStats s = e->st;
+    s.rc = result;
+    s.complete = complete ? 1 : 0;
+    s.depth = s.num_levels;
+    s.queue = complete ? 0 : e->n_cur;
+    if (bad_id != ~0ull && trace_out && e->trace) {
+        int n = vsr_engine_build_trace(e, bad_id, trace_out, trace_actions, trace_cap);
+        s.trace_len = n > 0 ? n : 0;
+    }
+    s.seconds_total = now_s() - t0;
+    *stats = s;
+    if (rc && opts->verbose) fprintf(stderr, "vsr_bfs: %s\n", e->last_error);
+    vsr_engine_destroy(e);
+    return result;
+}
+
+int vsr_probe_bench(int, uint64_t, uint64_t, double, int, double*) { return VSR_RC_ERROR; }
+
+} /* extern "C" */

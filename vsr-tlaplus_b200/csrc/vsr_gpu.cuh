@@ -1,0 +1,438 @@
+/*
+ * vsr_gpu.cuh — device side of the BFS wavefront (sm_100a).
+ *
+ * One launch of expand_kernel<L> = TLC's worker loop (SURVEY §3.1 / §8a stages E1-E9) over one BFS
+ * level of packed VSR.tla states:
+ *   E1  successor enumeration   Ops<L>::step over the candidate (action, binding) index space
+ *   E2  SYMMETRY                kept incrementally by step (canonical value labels)
+ *   E3  VIEW                    mask of the aux bits inside fp64_view
+ *   E4  fingerprint             FP64 (Rabin) of the packed VIEW bytes + a 32-bit check hash
+ *   E5  seen-set                open-addressed HBM table of 16-byte {fp, meta} entries, one 128-bit load per
+ *                               probe, insertion by one 128-bit CAS (ATOMG.E.CAS.128)
+ *   E6  queue                   next frontier staged per warp in shared memory, flushed 32 states at a time
+ *                               by a TMA bulk store (cp.async.bulk.global.shared::cta, UBLKCP)
+ *   E7  invariant               evaluated inline on every newly inserted state
+ *   E8  trace                   (parent id, candidate) per new state
+ *   E9  deadlock                states with no enabled candidate
+ * Work shape: a warp takes 32 frontier states; every lane evaluates the GUARD of each
+ * candidate on its own state (uniform control flow: the candidate index is warp-uniform), enabled
+ * (lane, candidate) pairs are compacted into a warp queue, and whenever 32 are queued the whole warp
+ * applies them — one successor per lane — so the expensive part (apply, fingerprint, probe) runs
+ * with full lanes whatever the enabled-candidate density.
+ */
+#ifndef VSR_GPU_CUH
+#define VSR_GPU_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "vsr_actions.h"
+
+namespace vsr {
+
+struct DevCounters {
+    unsigned long long out_count;   /* states appended to the next frontier this level */
+    unsigned long long generated;   /* successors generated (TLC's count: one per binding) */
+    unsigned long long ties;        /* same-level VIEW ties with a different aux key */
+    unsigned long long collisions;  /* fp equal, check hash different */
+    unsigned long long probes;      /* table entries inspected */
+    unsigned long long viol_id;     /* smallest global id of a violating new state (~0 = none) */
+    unsigned long long dead_id;     /* smallest global id of an expanded state without successors */
+    unsigned long long work_next;   /* next 32-state chunk to hand out */
+    unsigned long long tie_count;   /* entries in the tie list */
+    int error;                      /* first E_* raised */
+    int overflow;                   /* next frontier / send buffer / tie list full */
+    int viol_which;                 /* mask bit of the violated invariant */
+    int _pad;
+};
+
+struct TieRec {
+    uint64_t fp;
+    uint64_t parent;
+    uint32_t auxkey, cand, check, _pad;
+};
+
+/* record shipped to the owner rank of a successor: state words, then this header */
+struct RecHdr {
+    uint64_t fp;
+    uint64_t meta;
+    uint64_t parent; /* global id: rank << 40 | local id */
+    uint32_t cand, mult;
+};
+
+struct ExpandParams {
+    const uint32_t* in;          /* current frontier, n_in states of L::NW words */
+    unsigned long long n_in;
+    unsigned long long in_base;  /* local id of in[0] */
+    uint32_t* out;               /* next frontier */
+    unsigned long long out_cap;
+    unsigned long long out_base; /* local id of out[0] */
+    uint64_t* table;             /* capacity entries of {fp, meta} */
+    unsigned long long table_mask;
+    uint64_t* trace;             /* per local id: make_trec(parent global id, candidate); may be null */
+    unsigned long long trace_cap;
+    DevCounters* ctr;
+    TieRec* ties;
+    unsigned long long tie_cap;
+    const uint64_t* fp_tab;      /* 256-entry FP64 byte table */
+    RunCfg run;
+    int level;                   /* depth of the states being GENERATED (Init = 1) */
+    int check_deadlock;
+    int rank, world, owner_shift;/* owner(fp) = fp >> owner_shift (world a power of two; 64 when world = 1) */
+    uint8_t* send;               /* world * send_cap records of (L::BYTES + sizeof(RecHdr)) */
+    unsigned long long send_cap;
+    unsigned int* send_count;    /* world counters */
+};
+
+struct InsertParams {
+    const uint8_t* recs;
+    unsigned long long n;
+    ExpandParams e;              /* table / out / trace / counters as above */
+};
+
+/* ------------------------------------------------------------------ primitives */
+
+__device__ __forceinline__ void cas128(uint64_t* p, uint64_t s0, uint64_t s1, uint64_t& o0, uint64_t& o1) {
+    /* compare with {0,0} (empty slot), swap in {s0,s1}; returns the previous contents */
+    asm volatile(
+        "{\n\t.reg .b128 cmp, swp, old;\n\tmov.b128 cmp, {%2, %3};\n\tmov.b128 swp, {%4, %5};\n\t"
+        "atom.global.relaxed.gpu.cas.b128 old, [%6], cmp, swp;\n\tmov.b128 {%0, %1}, old;\n\t}"
+        : "=l"(o0), "=l"(o1)
+        : "l"(0ull), "l"(0ull), "l"(s0), "l"(s1), "l"(p)
+        : "memory");
+}
+__device__ __forceinline__ void ld128_cg(const uint64_t* p, uint64_t& a, uint64_t& b) {
+    asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ uint64_t mix64(uint64_t x) { /* splitmix64 finaliser: slot index from the fingerprint */
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ULL;
+    x ^= x >> 27; x *= 0x94d049bb133111ebULL;
+    x ^= x >> 31;
+    return x;
+}
+template <class L> __device__ __forceinline__ uint32_t check_hash(const uint32_t* w, bool use_view) {
+    /* second, independent 32-bit hash of the VIEW words: lets the seen-set tell fp64 collisions apart */
+    constexpr int full = L::VIEW_BITS >> 5, rem = L::VIEW_BITS & 31;
+    const int nw = use_view ? (full + (rem ? 1 : 0)) : L::NW;
+    uint32_t h = 0x9747b28cu;
+    for (int i = 0; i < nw; i++) {
+        uint32_t k = w[i];
+        if (use_view && i == full) k &= (1u << rem) - 1u;
+        k *= 0xcc9e2d51u; k = (k << 15) | (k >> 17); k *= 0x1b873593u;
+        h ^= k; h = (h << 13) | (h >> 19); h = h * 5u + 0xe6546b64u;
+    }
+    h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+    return h;
+}
+
+enum { INS_NEW = 0, INS_DUP = 1, INS_TIE = 2 };
+
+/* global state id = rank << 40 | local id; trace record = global id of the parent << 12 | candidate index
+   (bit 63 is a transient "violates the invariant" mark inside the staging area) */
+__host__ __device__ __forceinline__ uint64_t make_gid(int rank, unsigned long long local_id) { return ((uint64_t)rank << 40) | local_id; }
+__host__ __device__ __forceinline__ uint64_t make_trec(uint64_t parent_gid, uint32_t cand) { return (parent_gid << 12) | (cand & 0xFFFu); }
+
+__device__ __forceinline__ uint64_t make_meta(int level, uint32_t auxkey, uint32_t check) {
+    return ((uint64_t)(uint32_t)level << 56) | ((uint64_t)(auxkey & 0xFFFFFFu) << 32) | check;
+}
+
+/* lock-free insert-if-absent; linear probing over 16-byte entries */
+__device__ __forceinline__ int table_insert(uint64_t* table, unsigned long long mask, uint64_t fp, uint64_t meta,
+                                            unsigned& probes, unsigned& collisions) {
+    unsigned long long h = mix64(fp) & mask;
+    for (;;) {
+        uint64_t e0, e1;
+        ld128_cg(table + 2 * h, e0, e1);
+        probes++;
+        if (e0 == 0) {
+            cas128(table + 2 * h, fp, meta, e0, e1);
+            if (e0 == 0 && e1 == 0) return INS_NEW;
+        } else if (e1 == 0) {
+            continue; /* torn read of an entry being published: look again */
+        }
+        if (e0 == fp) {
+            if ((uint32_t)e1 == (uint32_t)meta) {
+                const bool same_level = (e1 >> 56) == (meta >> 56);
+                const bool same_aux = ((e1 >> 32) & 0xFFFFFF) == ((meta >> 32) & 0xFFFFFF);
+                return (same_level && !same_aux) ? INS_TIE : INS_DUP;
+            }
+            collisions++;
+        }
+        h = (h + 1) & mask;
+    }
+}
+
+/* TMA bulk store shared -> global of `bytes` (multiple of 16), issued by one lane; waits until the
+   shared source may be overwritten */
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+/* ------------------------------------------------------------------ expand kernel */
+
+constexpr int EXP_WARPS = 8; /* warps per block */
+constexpr int QCAP = 64;     /* (lane, candidate) queue per warp */
+constexpr int SCAP = 64;     /* staged new states per warp */
+
+template <class L> struct WarpSmem {
+    uint32_t par[32 * (L::NW + 1)];              /* this warp's 32 parent states, row stride NW+1 (bank-conflict-free) */
+    alignas(16) uint32_t stage[SCAP * L::NW];    /* new states, packed back to back for the bulk store */
+    unsigned long long tstage[SCAP];             /* their trace records */
+    uint32_t queue[QCAP];
+};
+template <class L> struct BlockSmem {
+    uint64_t fp_tab[256];
+    WarpSmem<L> w[EXP_WARPS];
+};
+
+template <class L> struct Expander {
+    typedef Ops<L> O_;
+    const ExpandParams& P;
+    WarpSmem<L>& S;
+    const uint64_t* tab;
+    const int lane;
+    int qn = 0, sn = 0;
+    unsigned long long gen = 0;
+    unsigned probes = 0, coll = 0, ties = 0;
+    unsigned long long chunk_first = 0; /* index in P.in of lane 0's parent */
+
+    __device__ Expander(const ExpandParams& p, WarpSmem<L>& s, const uint64_t* t, int ln) : P(p), S(s), tab(t), lane(ln) {}
+
+    /* flush the first n staged states (n <= 32) to the next frontier: one atomicAdd for the block of
+       ids, one TMA bulk store for the states, then move the remainder (< 32 states) down */
+    __device__ void flush(int n) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&P.ctr->out_count, (unsigned long long)n);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane < n) {
+            const unsigned long long t = S.tstage[lane];
+            if (t >> 63) { /* marked by the inline invariant check; now the id is known */
+                atomicMin(&P.ctr->viol_id, P.out_base + base + lane);
+                S.tstage[lane] = t & ~(1ull << 63);
+            }
+        }
+        __syncwarp();
+        if (base + n > P.out_cap) {
+            if (lane == 0) atomicExch(&P.ctr->overflow, 1);
+        } else {
+            if (lane == 0) bulk_store(P.out + base * L::NW, S.stage, (uint32_t)(n * L::BYTES));
+            if (P.trace && lane < n && P.out_base + base + lane < P.trace_cap) P.trace[P.out_base + base + lane] = S.tstage[lane];
+        }
+        __syncwarp();
+        const int rest = sn - n;
+        for (int i0 = 0; i0 < rest * L::NW; i0 += 32) {
+            const int i = i0 + lane;
+            uint32_t v = 0;
+            if (i < rest * L::NW) v = S.stage[n * L::NW + i];
+            __syncwarp();
+            if (i < rest * L::NW) S.stage[i] = v;
+        }
+        unsigned long long t = 0;
+        if (lane < rest) t = S.tstage[n + lane];
+        __syncwarp();
+        if (lane < rest) S.tstage[lane] = t;
+        sn = rest;
+        __syncwarp();
+    }
+
+    /* apply the first k queued (lane, candidate) pairs, one per lane */
+    __device__ void drain(int k) {
+        uint32_t n[L::NW];
+        bool isnew = false;
+        int bad = 0;
+        unsigned long long trec = 0;
+        if (lane < k) {
+            const uint32_t item = S.queue[lane];
+            const int pl = item & 31, cand = item >> 5;
+            const uint32_t* parent = &S.par[pl * (L::NW + 1)];
+            const int mult = O_::template step<true>(P.run, parent, cand, n);
+            if (mult < 0) {
+                atomicCAS(&P.ctr->error, 0, mult);
+            } else if (mult > 0) {
+                gen += (unsigned long long)mult;
+                uint64_t fp = fp64_view<L>(tab, n, P.run.use_view != 0);
+                if (fp == 0) fp = 1;
+                const uint32_t chk = check_hash<L>(n, P.run.use_view != 0);
+                const uint32_t auxkey = O_::aux_key(n);
+                const uint64_t meta = make_meta(P.level, auxkey, chk);
+                const uint64_t parent_gid = make_gid(P.rank, P.in_base + chunk_first + pl);
+                trec = make_trec(parent_gid, (uint32_t)cand);
+                const int owner = P.world > 1 ? (int)(fp >> P.owner_shift) : P.rank;
+                if (owner == P.rank) {
+                    const int r = table_insert(P.table, P.table_mask, fp, meta, probes, coll);
+                    isnew = r == INS_NEW;
+                    if (isnew) bad = O_::invariant(P.run, n);
+                    if (r == INS_TIE) {
+                        ties++;
+                        const unsigned long long t = atomicAdd(&P.ctr->tie_count, 1ull);
+                        if (t < P.tie_cap) {
+                            TieRec rec;
+                            rec.fp = fp; rec.parent = parent_gid; rec.auxkey = auxkey; rec.cand = (uint32_t)cand; rec.check = chk; rec._pad = 0;
+                            P.ties[t] = rec;
+                        } else atomicExch(&P.ctr->overflow, 2);
+                    }
+                } else {
+                    const unsigned idx = atomicAdd(&P.send_count[owner], 1u);
+                    if (idx < P.send_cap) {
+                        uint8_t* rec = P.send + ((size_t)owner * P.send_cap + idx) * (L::BYTES + sizeof(RecHdr));
+                        uint32_t* rw = (uint32_t*)rec;
+                        for (int j = 0; j < L::NW; j++) rw[j] = n[j];
+                        RecHdr* h = (RecHdr*)(rec + L::BYTES);
+                        h->fp = fp; h->meta = meta; h->parent = parent_gid; h->cand = (uint32_t)cand; h->mult = (uint32_t)mult;
+                    } else atomicExch(&P.ctr->overflow, 3);
+                }
+            }
+        }
+        /* compaction of the survivors into the warp's staging area (one ballot, all lanes) */
+        const unsigned newmask = __ballot_sync(0xffffffffu, isnew);
+        if (isnew) {
+            const int slot = sn + __popc(newmask & ((1u << lane) - 1u));
+            for (int j = 0; j < L::NW; j++) S.stage[slot * L::NW + j] = n[j];
+            if (bad) {
+                trec |= 1ull << 63;
+                atomicOr(&P.ctr->viol_which, bad);
+            }
+            S.tstage[slot] = trec;
+        }
+        sn += __popc(newmask);
+        __syncwarp();
+        while (sn >= 32) flush(32);
+        /* shift the queue */
+        const int rest = qn - k;
+        uint32_t q = 0;
+        if (lane < rest) q = S.queue[k + lane];
+        __syncwarp();
+        if (lane < rest) S.queue[lane] = q;
+        qn = rest;
+        __syncwarp();
+    }
+
+    __device__ void run_chunk(unsigned long long first, int count) {
+        chunk_first = first;
+        /* coalesced load of `count` parent states into padded rows */
+        const uint32_t* src = P.in + first * L::NW;
+        for (int i = lane; i < count * L::NW; i += 32) S.par[(i / L::NW) * (L::NW + 1) + (i % L::NW)] = __ldg(src + i);
+        __syncwarp();
+        uint32_t mine[L::NW];
+        const bool have = lane < count;
+        if (have) {
+            for (int j = 0; j < L::NW; j++) mine[j] = S.par[lane * (L::NW + 1) + j];
+        } else {
+            for (int j = 0; j < L::NW; j++) mine[j] = 0;
+        }
+        bool any = false;
+        for (int cand = 0; cand < L::NCAND; cand++) {
+            int m = 0;
+            if (have) m = O_::template step<false>(P.run, mine, cand, nullptr);
+            const unsigned en = __ballot_sync(0xffffffffu, m > 0);
+            if (en) {
+                if (m > 0) {
+                    any = true;
+                    S.queue[qn + __popc(en & ((1u << lane) - 1u))] = (uint32_t)lane | ((uint32_t)cand << 5);
+                }
+                qn += __popc(en);
+                __syncwarp();
+                if (qn >= 32) drain(32);
+            }
+        }
+        if (qn > 0) drain(qn);
+        if (P.check_deadlock && have && !any) atomicMin(&P.ctr->dead_id, P.in_base + first + lane);
+    }
+
+    __device__ void finish() {
+        while (sn > 0) flush(sn < 32 ? sn : 32);
+        /* per-warp totals */
+        for (int o = 16; o; o >>= 1) {
+            gen += __shfl_xor_sync(0xffffffffu, gen, o);
+            probes += __shfl_xor_sync(0xffffffffu, probes, o);
+            coll += __shfl_xor_sync(0xffffffffu, coll, o);
+            ties += __shfl_xor_sync(0xffffffffu, ties, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&P.ctr->generated, gen);
+            atomicAdd(&P.ctr->probes, (unsigned long long)probes);
+            if (coll) atomicAdd(&P.ctr->collisions, (unsigned long long)coll);
+            if (ties) atomicAdd(&P.ctr->ties, (unsigned long long)ties);
+        }
+    }
+};
+
+template <class L> __global__ void __launch_bounds__(EXP_WARPS * 32) expand_kernel(const ExpandParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    BlockSmem<L>& B = *reinterpret_cast<BlockSmem<L>*>(smem_raw);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) B.fp_tab[i] = P.fp_tab[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    Expander<L> X(P, B.w[warp], B.fp_tab, lane);
+    const unsigned long long nchunks = (P.n_in + 31) / 32;
+    for (;;) {
+        unsigned long long c = 0;
+        if (lane == 0) c = atomicAdd(&P.ctr->work_next, 1ull);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        if (c >= nchunks) break;
+        const unsigned long long first = c * 32;
+        const int count = (int)((P.n_in - first) < 32 ? (P.n_in - first) : 32);
+        X.run_chunk(first, count);
+    }
+    X.finish();
+}
+
+/* ------------------------------------------------------------------ insert kernel (records from peers, and Init) */
+
+template <class L> __global__ void __launch_bounds__(256) insert_kernel(const InsertParams Q) {
+    const ExpandParams& P = Q.e;
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool have = i < Q.n;
+    bool isnew = false;
+    const uint8_t* rec = Q.recs + (have ? i : 0) * (L::BYTES + sizeof(RecHdr));
+    const uint32_t* n = (const uint32_t*)rec;
+    const RecHdr* h = (const RecHdr*)(rec + L::BYTES);
+    unsigned probes = 0, coll = 0;
+    if (have) {
+        /* meta == 0: the sender (host seeding Init) left tag computation to the device */
+        const uint64_t meta = h->meta ? h->meta : make_meta(P.level, Ops<L>::aux_key(n), check_hash<L>(n, P.run.use_view != 0));
+        const int r = table_insert(P.table, P.table_mask, h->fp, meta, probes, coll);
+        isnew = r == INS_NEW;
+        atomicAdd(&P.ctr->generated, (unsigned long long)h->mult);
+        if (r == INS_TIE) {
+            atomicAdd(&P.ctr->ties, 1ull);
+            const unsigned long long t = atomicAdd(&P.ctr->tie_count, 1ull);
+            if (t < P.tie_cap) {
+                TieRec tr;
+                tr.fp = h->fp; tr.parent = h->parent; tr.auxkey = (uint32_t)((meta >> 32) & 0xFFFFFF); tr.cand = h->cand;
+                tr.check = (uint32_t)meta; tr._pad = 0;
+                P.ties[t] = tr;
+            } else atomicExch(&P.ctr->overflow, 2);
+        }
+        if (coll) atomicAdd(&P.ctr->collisions, (unsigned long long)coll);
+        atomicAdd(&P.ctr->probes, (unsigned long long)probes);
+    }
+    const unsigned newmask = __ballot_sync(0xffffffffu, isnew);
+    if (newmask) {
+        unsigned long long base = 0;
+        const int leader = __ffs(newmask) - 1;
+        if (lane == leader) base = atomicAdd(&P.ctr->out_count, (unsigned long long)__popc(newmask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (isnew) {
+            const unsigned long long pos = base + __popc(newmask & ((1u << lane) - 1u));
+            if (pos < P.out_cap) {
+                uint32_t* dst = P.out + pos * L::NW;
+                for (int j = 0; j < L::NW; j++) dst[j] = n[j];
+                if (P.trace && P.out_base + pos < P.trace_cap) P.trace[P.out_base + pos] = make_trec(h->parent, h->cand);
+                const int bad = Ops<L>::invariant(P.run, n);
+                if (bad) {
+                    atomicMin(&P.ctr->viol_id, P.out_base + pos);
+                    atomicOr(&P.ctr->viol_which, bad);
+                }
+            } else atomicExch(&P.ctr->overflow, 1);
+        }
+    }
+}
+
+} // namespace vsr
+#endif
