@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""bench.py — unique states explored per second for VSR.tla (BASELINE.json's metric).
+
+Workload (config.workload): BASELINE configs[1] = the reference's shipped VSR.cfg — ReplicaCount=3, ClientCount=1,
+Values={v1,v2}, StartViewOnTimerLimit=2, VIEW view, SYMMETRY symmValues, INVARIANT AcknowledgedWriteNotLost,
+deadlock checking off, exploration continued past the violation to the COMPLETE reachable set (1,173,992,337
+distinct states, depth 47).  One "step" = one complete BFS of that state space.  Inputs are fully determined
+by the config (single Init state): "synthetic" data does not apply; nothing is cached between steps — every
+step clears the seen-set and starts from Init.
+
+  value   distinct states / second, device-timed over K steps with the engine (tables allocated) resident in HBM
+  e2e     the same metric through the public one-call API (ModelChecker.check -> vsr_bfs): config text in host
+          memory -> parse -> allocate -> BFS -> stats and counterexample back in host memory
+  --impl reference   the CPU restatement of the spec (oracle/, "port": TLC itself cannot run here — no JVM) on all
+          host cores, bounded sample per step
+
+Launch: python bench.py --gpus N --steps K --warmup W   (N>1: under torchrun, one rank per GPU, NCCL).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(R=3, V=2, L=2)           # BASELINE configs[1] = vsr-revisited/paper/VSR.cfg
+TABLE_CAP = 1 << 31                      # 2^31 slots * 16 B = 32 GiB (1.17e9 states -> load 0.55)
+FRONTIER_CAP = 140_000_000               # widest level: 120,193,500 states
+EXPECT = dict(distinct=1173992337, generated=3129587684, depth=47, violation_level=28)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_sample(seconds, workers):
+    """CPU restatement (oracle/) on the same workload for a bounded time: distinct states / s on `workers` threads."""
+    so = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+    lib = C.CDLL(so)
+    lib.orc_bfs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_double, C.c_int, C.c_int, C.c_int, C.c_char_p,
+                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    q = (C.c_int * 8)(WORKLOAD["R"], 1, WORKLOAD["V"], WORKLOAD["L"], 0, 1, 1, 0)  # invariant 0: explore, do not stop
+    scal = (C.c_uint64 * 32)()
+    lv = (C.c_uint64 * 512)()
+    t0 = time.time()
+    lib.orc_bfs(q, workers, 0, 0, float(seconds), 0, 0, 0, None, scal, lv, None, 512, None, None, 0)
+    dt = time.time() - t0
+    return dict(distinct=int(scal[1]), generated=int(scal[0]), depth=int(scal[3]), seconds=dt, rate=int(scal[1]) / dt)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = 10.0
+    for _ in range(args.warmup):
+        oracle_sample(1.0, cores)
+    tot_states, tot_s = 0, 0.0
+    sample = None
+    for _ in range(args.steps):
+        sample = oracle_sample(per_step, cores)
+        tot_states += sample["distinct"]
+        tot_s += sample["seconds"]
+    v = tot_states / tot_s
+    desc = "BFS of the same config from Init for %.0f s wall per step (reaches depth %d, %d distinct states)" % (
+        per_step, sample["depth"], sample["distinct"])
+    print(json.dumps({
+        "impl": "reference", "metric": "unique states explored/sec (VSR.tla, shipped VSR.cfg constants)", "value": v, "unit": "states/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "none (state space of the config)",
+        "config": {"workload": "VSR.tla ReplicaCount=3 ClientCount=1 Values={v1,v2} StartViewOnTimerLimit=2 (BASELINE configs[1]), "
+                               "bounded sample of the BFS", "note": "CPU restatement of the spec (oracle/), NOT TLC: no JVM in this image"},
+        "cpu_baseline": {"value": v, "unit": "states/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": v, "unit": "states/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import _pkg
+    pkg = _pkg.load()
+    from vsr_tlaplus_b200 import dist as vdist
+    import torch.distributed as tdist
+
+    if world > 1:
+        torch.cuda.set_device(local)
+        tdist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert world == args.gpus, "launch with torchrun --nproc-per-node == --gpus"
+    dev = torch.device("cuda", local)
+
+    cfg = pkg.cfg_text(WORKLOAD["R"], ["v1", "v2"], WORKLOAD["L"])
+    mc = pkg.ModelChecker.from_cfg_text(cfg)
+    S = mc.state_bytes
+    table_cap = TABLE_CAP // world
+    frontier_cap = FRONTIER_CAP // world + 4_000_000
+    send_cap = max(1, (FRONTIER_CAP * 3) // (world * world)) if world > 1 else 1
+    eng = vdist.GpuEngine(mc, rank, world, device=local, table_capacity=table_cap, frontier_capacity=frontier_cap,
+                          send_capacity=send_cap, keep_trace=True)
+    bfs = vdist.ShardedBfs(eng, rank, world)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def one_step():
+        return bfs.run(stop_on_violation=False, want_trace=False)
+
+    for _ in range(args.warmup):
+        res = one_step()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    st0 = eng.stats()
+    launches0 = 0
+    ev0.record()
+    t0 = time.time()
+    kernel_ms = 0.0
+    levels_ms = []
+    for _ in range(args.steps):
+        res = one_step()
+        kernel_ms += res.kernel_ms_max
+        st = eng.stats()
+        launches0 += int(st.kernel_launches)
+        levels_ms.append([float(st.level_ms[i]) for i in range(int(st.num_levels))])
+    ev1.record()
+    barrier()
+    wall = time.time() - t0
+    dev_ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([wall, dev_ms / 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+    wall = float(t[0])
+    clocks = sampler.stop() if rank == 0 else None
+
+    ok = (res.distinct == EXPECT["distinct"] and res.generated == EXPECT["generated"] and res.depth == EXPECT["depth"] and
+          res.violation_level == EXPECT["violation_level"] and res.complete)
+    value = res.distinct * args.steps / wall
+
+    # roofline of the dominant kernel (expand_kernel): algorithmic bytes per distinct state
+    g = res.generated / res.distinct
+    b_alg = 2 * S + 32 * g + 32 + 8          # read + write the packed state, one 32 B sector per probe, the CAS sector, trace record
+    kern_s = kernel_ms / 1e3                 # sum over levels of the slowest rank's kernel time, all timed steps
+    achieved = (res.distinct / world) * args.steps * b_alg / kern_s / 1e9
+    peak, peak_src = peaks()
+
+    # e2e: the public one-call API with host buffers in and out (N=1: vsr_bfs; N>1: the same pump incl. engine creation)
+    eng.close()
+    del eng
+    torch.cuda.empty_cache()
+    barrier()
+    te = time.time()
+    if world == 1:
+        r2 = pkg.ModelChecker.from_cfg_text(cfg).check(stop_on_violation=False, table_capacity=table_cap, frontier_capacity=frontier_cap)
+        e2e_states, h2d, d2h = r2.distinct, r2.bytes_h2d + len(cfg), r2.bytes_d2h + C.sizeof(pkg.checker.VsrStats)
+        ok = ok and r2.distinct == EXPECT["distinct"] and r2.rc == 12 and len(r2.trace) == EXPECT["violation_level"]
+    else:
+        mc2 = pkg.ModelChecker.from_cfg_text(cfg)
+        eng2 = vdist.GpuEngine(mc2, rank, world, device=local, table_capacity=table_cap, frontier_capacity=frontier_cap,
+                               send_capacity=send_cap, keep_trace=True)
+        r2 = vdist.ShardedBfs(eng2, rank, world).run(stop_on_violation=False, want_trace=True)
+        st2 = eng2.stats()
+        e2e_states, h2d, d2h = r2.distinct, int(st2.bytes_h2d) + len(cfg), int(st2.bytes_d2h)
+        eng2.close()
+    barrier()
+    e2e_s = time.time() - te
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+    e2e_s = float(t[0])
+
+    if rank == 0:
+        out = {
+            "metric": "unique states explored/sec (VSR.tla, shipped VSR.cfg constants)", "value": value, "unit": "states/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
+            "data": "none: the workload is the complete reachable state space of the config (single Init state)",
+            "config": {"workload": "VSR.tla ReplicaCount=3 ClientCount=1 Values={v1,v2} StartViewOnTimerLimit=2 VIEW view SYMMETRY symmValues "
+                                   "INVARIANT AcknowledgedWriteNotLost, deadlock check off, continued past the violation to the complete "
+                                   "reachable set (BASELINE configs[1] = shipped VSR.cfg)",
+                       "state_bytes": S, "distinct_states": res.distinct, "states_generated": res.generated, "depth": res.depth,
+                       "first_violation_depth": res.violation_level, "parallelism": "fingerprint-sharded x%d" % world,
+                       "l2": "working set (seen-set %.1f GiB) exceeds L2; no flush needed" % (table_cap * 16 / 2**30),
+                       "results_match_expected": bool(ok), "timing": "wall clock bracketed by barrier+synchronize, max over ranks; "
+                       "device time between CUDA events on the launch stream = %.3f s" % (dev_ms / 1e3)},
+            "gpu_launches": launches0,
+            "kernel_seconds": kern_s,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "bytes_per_state": b_alg, "g": g,
+                         "kernel": "expand_kernel<Layout<3,2,3>> (per-GPU states x B_alg / sum of per-level kernel time, max over ranks)"},
+            "e2e": {"value": e2e_states / e2e_s, "unit": "states/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "seconds": e2e_s, "api": "ModelChecker.from_cfg_text(cfg).check()" if world == 1 else "dist.GpuEngine + dist.ShardedBfs.run()"},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            s = oracle_sample(args.cpu_seconds, cores)
+            out["cpu_baseline"] = {"value": s["rate"], "unit": "states/s", "cores": cores, "kind": "port",
+                                   "sample": "CPU restatement (oracle/, not TLC) BFS of the same config for %.0f s: depth %d, %d distinct states"
+                                             % (args.cpu_seconds, s["depth"], s["distinct"])}
+        print(json.dumps(out))
+    if world > 1:
+        tdist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -71,6 +71,8 @@ int vsr_init(const VsrModel* m, void* state_out);                        /* Init
  * action_ids[i] = VSR_ACT_*, mult[i] = TLC bindings that successor stands for; returns the number
  * of successors, or a negative E_* code if one cannot be represented. */
 int vsr_successors(const VsrModel* m, const void* state, void* out, size_t cap, uint8_t* action_ids, uint32_t* mult);
+/* candidate (action, binding) indices whose guard holds in `state`, in the order vsr_successors emits them */
+int vsr_enabled_candidates(const VsrModel* m, const void* state, uint32_t* out, size_t cap);
 int vsr_canon(const VsrModel* m, void* state);                           /* SYMMETRY representative, VSR.tla:151 */
 uint64_t vsr_fingerprint(const VsrModel* m, const void* state);          /* FP64 of the VIEW projection, VSR.tla:149-150 */
 uint32_t vsr_aux_key(const VsrModel* m, const void* state);
@@ -123,6 +125,8 @@ typedef struct VsrStats {
     uint64_t violation_id;
     uint64_t table_capacity, frontier_capacity;
     uint64_t bytes_table, bytes_frontier;
+    uint64_t bytes_h2d, bytes_d2h;         /* host<->device bytes moved by the engine (inputs, per-level counters, trace reads) */
+    double seconds_setup;                 /* engine creation: allocation + clearing the seen-set */
 } VsrStats;
 
 typedef struct VsrEngine VsrEngine;
@@ -161,6 +165,8 @@ int vsr_engine_read_frontier(VsrEngine* e, uint64_t first, uint64_t n, void* hos
 /* trace record of a locally owned state id: parent global id (rank << 48 | local id) and candidate index */
 int vsr_engine_trace_record(VsrEngine* e, uint64_t local_id, uint64_t* parent_out, uint32_t* cand_out);
 int vsr_engine_stats(const VsrEngine* e, VsrStats* out);
+/* forget everything explored (clears the seen-set, keeps the allocations): ready for seed_init again */
+int vsr_engine_reset(VsrEngine* e);
 const char* vsr_engine_last_error(const VsrEngine* e);
 /* with opts.collect_levels: number of states first seen at depth `level` (1-based) and, if host_out has room, a copy */
 uint64_t vsr_engine_collected(const VsrEngine* e, int level, void* host_out, uint64_t cap_states);

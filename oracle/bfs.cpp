@@ -201,7 +201,7 @@ BfsResult bfs(const Params& p, const BfsOptions& o) {
         uint64_t new_base = frontier_base + frontier.size();
         std::vector<std::string> next_frontier;
         next_frontier.reserve(fresh.size());
-        if (dig_file && !stopped_early) {
+        if (dig_file && !stopped_early && !fresh.empty()) {
             uint64_t n = fresh.size();
             fwrite(&n, 8, 1, dig_file);
             for (Cand* c : fresh) fwrite(&c->d, 16, 1, dig_file);

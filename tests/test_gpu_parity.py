@@ -105,9 +105,9 @@ def test_counterexample_is_a_behaviour(pkg):
     """AcknowledgedWritesExistOnMajority is violated early; the GPU's counterexample must be a literal behaviour
     of the spec (every step in the oracle's Next, last state violating), of minimal length (BFS)."""
     inv = ("AcknowledgedWritesExistOnMajority",)
-    mc = pkg.ModelChecker.from_constants(3, 2, 2, invariants=inv)
+    mc = pkg.ModelChecker.from_constants(3, 2, 1, invariants=inv)
     res = mc.check(table_capacity=1 << 22, frontier_capacity=1 << 20)
-    q = orc.params(3, 2, 2, invariant=2)
+    q = orc.params(3, 2, 1, invariant=2)
     o = orc.bfs(q, workers=8, keep_trace=False)
     if o.rc != 12:
         pytest.skip("invariant not violated in this configuration")
@@ -122,8 +122,8 @@ def test_counterexample_is_a_behaviour(pkg):
         succ = (pkg.checker.VsrFlatState * cap)()
         acts = (C.c_int * cap)()
         n = L.orc_successors_flat(q, C.byref(flats[i]), succ, acts, cap)
-        want = orc.digests_full_of(orc.params(3, 2, 2, symmetry=False, invariant=2), (pkg.checker.VsrFlatState * 1)(flats[i + 1]))[0]
-        got = orc.digests_full_of(orc.params(3, 2, 2, symmetry=False, invariant=2), succ)[:n]
+        want = orc.digests_full_of(orc.params(3, 2, 1, symmetry=False, invariant=2), (pkg.checker.VsrFlatState * 1)(flats[i + 1]))[0]
+        got = orc.digests_full_of(orc.params(3, 2, 1, symmetry=False, invariant=2), succ)[:n]
         names = [pkg.ACTION_NAMES[acts[k]] for k in range(n)]
         assert any(g == want and nm == res.trace[i + 1][0] for g, nm in zip(got, names)), f"step {i + 1} is not a step of Next"
     assert L.orc_invariant_flat(q, C.byref(flats[-1])) == 0

@@ -1,0 +1,182 @@
+"""CPU parity (no GPU): the product's packed Next / canonical labels / fingerprint vs the oracle, and the oracle
+against hand-derivable facts.  Sized to run in about a minute."""
+import ctypes as C
+import itertools
+import json
+import os
+import subprocess
+
+import pytest
+
+import orc
+from conftest import ROOT
+
+DIFF = os.path.join(ROOT, "build", "diff_host")
+
+
+def run_diff(*args):
+    if not os.path.exists(DIFF):
+        import __graft_entry__
+        __graft_entry__.build()
+    r = subprocess.run([DIFF] + [str(a) for a in args], capture_output=True, text=True, timeout=900)
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert r.returncode == 0, (out, r.stderr[-2000:])
+    return out
+
+
+@pytest.mark.parametrize("R,V,L,sym,n", [(2, 1, 1, 0, 10**6), (2, 2, 2, 1, 10**6), (2, 2, 2, 0, 10**6), (3, 1, 1, 0, 10**6)])
+def test_packed_next_equals_oracle_on_complete_spaces(R, V, L, sym, n):
+    out = run_diff(R, V, L, sym, n)
+    assert out["complete"] == 1 and out["mismatches"] == 0 and out["assumption_violations"] == 0
+
+
+@pytest.mark.parametrize("R,V,L,sym", [(3, 2, 2, 1), (3, 3, 3, 1), (5, 2, 2, 1), (3, 3, 3, 0), (4, 2, 2, 1), (3, 3, 2, 1)])
+def test_packed_next_equals_oracle_bfs_prefix(R, V, L, sym):
+    out = run_diff(R, V, L, sym, 12000)
+    assert out["checked"] == 12000 and out["mismatches"] == 0
+
+
+@pytest.mark.parametrize("R,V,L,sym,seed", [(3, 2, 2, 1, 1), (3, 3, 3, 1, 2), (5, 2, 2, 1, 3), (3, 3, 3, 0, 4), (3, 2, 2, 0, 5)])
+def test_packed_next_equals_oracle_on_random_walks(R, V, L, sym, seed):
+    """simulation-style deep coverage: state transfer, view-change completion and log truncation only happen 15+ steps in"""
+    out = run_diff(R, V, L, sym, 12000, 1, 100000, seed)
+    assert out["mismatches"] == 0 and out["max_walk_depth"] >= 30
+
+
+def test_oracle_small_configs_ground_truth():
+    """BASELINE configs[0] and friends, full BFS under the oracle: the numbers every other test leans on"""
+    o = orc.bfs(orc.params(2, 1, 1, symmetry=False), workers=2)
+    assert (o.generated, o.distinct, o.queue, o.depth, o.complete, o.rc) == (100, 76, 0, 14, True, 0)
+    assert o.level_sizes == [1, 2, 3, 5, 8, 9, 9, 9, 9, 8, 6, 4, 2, 1]
+    o = orc.bfs(orc.params(2, 2, 2), workers=4)
+    assert (o.generated, o.distinct, o.depth, o.complete) == (2812, 2073, 27, True)
+    o = orc.bfs(orc.params(3, 1, 1, symmetry=False), workers=8)
+    assert (o.generated, o.distinct, o.depth, o.complete) == (118746, 43941, 24, True)
+    assert o.h2_ties == 0 and sum(o.assumptions) == 0
+    # level-1/2 sizes are hand-derivable: (R-1)+1 distinct successors of Init under symmetry
+    for (R, V, L) in [(2, 1, 1), (3, 2, 2), (3, 3, 3), (5, 2, 2)]:
+        o = orc.bfs(orc.params(R, V, L), workers=2, max_depth=2)
+        assert o.level_sizes == [1, (R - 1) + 1] and o.level_generated == [(R - 1) + V]
+
+
+def test_deadlock_exists_and_is_reported_by_the_oracle():
+    """VSR.tla has reachable terminal states, so TLC's default deadlock check would stop the run"""
+    o = orc.bfs(orc.params(2, 1, 1, symmetry=False), workers=1, check_deadlock=True)
+    assert o.rc == 11
+
+
+def test_canonical_labelling_is_a_canonical_form(pkg):
+    """for states reached by random exploration and EVERY permutation pi of Values:
+    canon(pack(pi(s))) == canon(pack(s)) — the fast key-sorted labelling picks one representative per orbit"""
+    mc = pkg.ModelChecker.from_constants(3, 3, 3, symmetry=True)
+    raw = pkg.ModelChecker.from_constants(3, 3, 3, symmetry=False)
+    import random
+    rnd = random.Random(7)
+    checked = 0
+    for walk in range(60):
+        s = raw.init_state()
+        for step in range(45):
+            succ = raw.successors(s)
+            if not succ:
+                break
+            s = rnd.choice(succ)[0]
+            f = raw.unpack(s)
+            base = mc.pack(f)
+            for perm in itertools.permutations([1, 2, 3]):
+                g = permute_flat(pkg, f, perm)
+                assert mc.pack(g) == base
+                checked += 1
+    assert checked > 5000
+
+
+def permute_flat(pkg, f, perm):
+    """apply a permutation of value ids to a VsrFlatState (test-side, independent of product and oracle code)"""
+    Flat = pkg.checker.VsrFlatState
+    g = Flat.from_buffer_copy(bytes(f))
+    m = lambda x: perm[x - 1] if 1 <= x <= len(perm) else x
+
+    def fix_msg(k):
+        if k.has_entry:
+            k.entry.operation = m(k.entry.operation)
+        for i in range(k.log_n):
+            k.log[i].operation = m(k.log[i].operation)
+
+    for r in range(g.R):
+        rep = g.rep[r]
+        for i in range(rep.log_n):
+            rep.log[i].operation = m(rep.log[i].operation)
+        for i in range(rep.n_svc):
+            fix_msg(rep.svc_recv[i])
+        for i in range(rep.n_dvc):
+            fix_msg(rep.dvc_recv[i])
+    for i in range(g.n_msgs):
+        fix_msg(g.msgs[i])
+    acked = [0] * len(perm)
+    for v in range(len(perm)):
+        acked[perm[v] - 1] = f.acked[v]
+    for v in range(len(perm)):
+        g.acked[v] = acked[v]
+    return g
+
+
+def gf2_mulmod(a, b, poly_full, deg=64):
+    r = 0
+    while b:
+        if b & 1:
+            r ^= a
+        b >>= 1
+        a <<= 1
+        if a >> deg:
+            a ^= poly_full
+    return r
+
+
+def test_fp64_polynomial_is_irreducible_and_table_is_rabin(pkg):
+    """FP64_POLY is TLC's Polys[0] recalled from memory (no TLC source here): check it IS an irreducible degree-64
+    polynomial over GF(2) (Rabin's test) and that the byte table implements polynomial reduction by it."""
+    poly = 0x911498AE0E66BAD6  # bit 63 = x^0 ... bit 0 = x^63, x^64 implicit
+    full = 1 << 64
+    for i in range(64):
+        if (poly >> (63 - i)) & 1:
+            full |= 1 << i
+    # x^(2^64) == x (mod p)  and  gcd(x^(2^32) - x, p) == 1
+    x = 2
+    t = x
+    powers = {}
+    for k in range(1, 65):
+        t = gf2_mulmod(t, t, full)
+        powers[k] = t
+    assert powers[64] == x
+
+    def gf2_mod(a, b):
+        db = b.bit_length()
+        while a.bit_length() >= db:
+            a ^= b << (a.bit_length() - db)
+        return a
+
+    def gf2_gcd(a, b):
+        while b:
+            a, b = b, gf2_mod(a, b)
+        return a
+    assert gf2_gcd(full, powers[32] ^ x) == 1
+    # fingerprint linearity over GF(2) (a Rabin fingerprint is affine: fp(a)^fp(b)^fp(c) == fp(a^b^c))
+    mc = pkg.ModelChecker.from_cfg_text(pkg.cfg_text(3, ["v1", "v2"], 2, view=False, symmetry=False))
+    s0 = mc.init_state()
+    succ = [t for t, _, _ in mc.successors(s0)]
+    a, b, c = s0, succ[0], succ[1]
+    x3 = bytes(p ^ q ^ r for p, q, r in zip(a, b, c))
+    assert mc.fingerprint(a) ^ mc.fingerprint(b) ^ mc.fingerprint(c) == mc.fingerprint(x3)
+
+
+def test_view_masks_aux_variables_out_of_the_fingerprint(pkg):
+    """VIEW view (VSR.tla:149-150) drops aux_svc / aux_client_acked: states differing only there share a fingerprint"""
+    mc = pkg.ModelChecker.from_constants(3, 2, 2, symmetry=True, view=True)
+    nv = pkg.ModelChecker.from_constants(3, 2, 2, symmetry=True, view=False)
+    s = mc.init_state()
+    f = mc.unpack(s)
+    f.aux_svc = 1
+    t = mc.pack(f)
+    assert t != s
+    assert mc.fingerprint(t) == mc.fingerprint(s)
+    assert nv.fingerprint(t) != nv.fingerprint(s)
+    assert mc.aux_key(t) != mc.aux_key(s)

@@ -109,6 +109,7 @@ class VsrStats(C.Structure):
         ("violation_level", C.c_int32), ("trace_len", C.c_int32), ("error_code", C.c_int32), ("_pad", C.c_int32),
         ("violation_id", C.c_uint64), ("table_capacity", C.c_uint64), ("frontier_capacity", C.c_uint64),
         ("bytes_table", C.c_uint64), ("bytes_frontier", C.c_uint64),
+        ("bytes_h2d", C.c_uint64), ("bytes_d2h", C.c_uint64), ("seconds_setup", C.c_double),
     ]
 
 
@@ -122,12 +123,12 @@ class VsrLevelInfo(C.Structure):
 
 # every symbol include/vsr_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = [
-    "vsr_load", "vsr_load_cfg_text", "vsr_model_create", "vsr_model_free", "vsr_model_info", "vsr_init", "vsr_successors",
+    "vsr_load", "vsr_load_cfg_text", "vsr_model_create", "vsr_model_free", "vsr_model_info", "vsr_init", "vsr_successors", "vsr_enabled_candidates",
     "vsr_canon", "vsr_fingerprint", "vsr_aux_key", "vsr_invariant", "vsr_unpack", "vsr_pack", "vsr_state_to_tla",
     "vsr_flat_to_tla", "vsr_action_name", "vsr_action_location", "vsr_bfs", "vsr_engine_create", "vsr_engine_destroy",
     "vsr_engine_record_bytes", "vsr_engine_set_send_buffers", "vsr_engine_seed_init", "vsr_engine_expand",
     "vsr_engine_insert_records", "vsr_engine_finish_level", "vsr_engine_frontier_size", "vsr_engine_read_frontier",
-    "vsr_engine_trace_record", "vsr_engine_stats", "vsr_engine_last_error", "vsr_engine_collected", "vsr_engine_build_trace",
+    "vsr_engine_trace_record", "vsr_engine_stats", "vsr_engine_reset", "vsr_engine_last_error", "vsr_engine_collected", "vsr_engine_build_trace",
     "vsr_replay_candidates", "vsr_probe_bench", "vsr_version",
 ]
 
@@ -180,6 +181,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.vsr_engine_read_frontier.argtypes = [vp, u64, u64, vp]
     lib.vsr_engine_trace_record.argtypes = [vp, u64, C.POINTER(u64), C.POINTER(C.c_uint32)]
     lib.vsr_engine_stats.argtypes = [vp, C.POINTER(VsrStats)]
+    lib.vsr_engine_reset.argtypes = [vp]
     lib.vsr_engine_last_error.argtypes = [vp]
     lib.vsr_engine_last_error.restype = cp
     lib.vsr_engine_collected.argtypes = [vp, C.c_int, vp, u64]
@@ -238,6 +240,9 @@ class CheckResult:
     error_code: int
     table_capacity: int
     frontier_capacity: int
+    bytes_h2d: int = 0
+    bytes_d2h: int = 0
+    seconds_setup: float = 0.0
     trace: List[Tuple[str, bytes]] = field(default_factory=list)  # (action name, packed state)
     levels: List[bytes] = field(default_factory=list)             # collect_levels: raw states per depth
 
@@ -412,7 +417,8 @@ class ModelChecker:
             h2_ties=int(st.h2_ties), fp_collisions=int(st.fp_collisions), probe_total=int(st.probe_total),
             kernel_launches=int(st.kernel_launches), seconds_total=float(st.seconds_total),
             seconds_kernels=float(st.seconds_kernels), violation_level=int(st.violation_level), error_code=int(st.error_code),
-            table_capacity=int(st.table_capacity), frontier_capacity=int(st.frontier_capacity), trace=trace or [], levels=levels or [])
+            table_capacity=int(st.table_capacity), frontier_capacity=int(st.frontier_capacity), bytes_h2d=int(st.bytes_h2d),
+            bytes_d2h=int(st.bytes_d2h), seconds_setup=float(st.seconds_setup), trace=trace or [], levels=levels or [])
 
     def check(self, **kw) -> CheckResult:
         """One-GPU BFS through the single C-ABI call ``vsr_bfs`` (counterexample included)."""

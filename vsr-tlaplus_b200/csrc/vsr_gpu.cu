@@ -214,6 +214,7 @@ int vsr_engine_create(const VsrModel* m, const VsrRunOpts* opts, int rank, int w
     e->st.frontier_capacity = fcap;
     e->st.bytes_table = tcap * 16;
     e->st.bytes_frontier = 2 * fcap * S;
+    e->st.bytes_h2d += 256 * 8;
     if ((ce = cudaStreamSynchronize(e->stream)) != cudaSuccess) return bail("sync", ce);
     *out = e;
     return 0;
@@ -267,6 +268,7 @@ int vsr_engine_seed_init(VsrEngine* e) {
     h->cand = 0;
     h->mult = 1;
     CK(cudaMemcpyAsync(e->init_rec, rec.data(), rec.size(), cudaMemcpyHostToDevice, e->stream));
+    e->st.bytes_h2d += rec.size();
     InsertParams q;
     fill_params(e, q.e);
     q.e.level = 1;
@@ -325,6 +327,7 @@ int vsr_engine_insert_records(VsrEngine* e, const void* dev_records, uint64_t n)
 int vsr_engine_finish_level(VsrEngine* e, VsrLevelInfo* out) {
     DevCounters c;
     CK(cudaMemcpyAsync(&c, e->ctr, sizeof c, cudaMemcpyDeviceToHost, e->stream));
+    e->st.bytes_d2h += sizeof c;
     CK(cudaStreamSynchronize(e->stream));
     VsrLevelInfo li;
     memset(&li, 0, sizeof li);
@@ -394,8 +397,19 @@ int vsr_engine_trace_record(VsrEngine* e, uint64_t local_id, uint64_t* parent_ou
     if (!e->trace || local_id >= e->trace_cap) return VSR_RC_ERROR;
     uint64_t t = 0;
     CK(cudaMemcpy(&t, e->trace + local_id, 8, cudaMemcpyDeviceToHost));
+    e->st.bytes_d2h += 8;
     *parent_out = t >> 12;
     *cand_out = (uint32_t)(t & 0xFFF);
+    return 0;
+}
+
+int vsr_engine_reset(VsrEngine* e) {
+    CK(cudaMemsetAsync(e->table, 0, e->table_cap * 16, e->stream));
+    const uint64_t tc = e->st.table_capacity, fc = e->st.frontier_capacity, bt = e->st.bytes_table, bf = e->st.bytes_frontier;
+    memset(&e->st, 0, sizeof e->st);
+    e->st.table_capacity = tc; e->st.frontier_capacity = fc; e->st.bytes_table = bt; e->st.bytes_frontier = bf;
+    e->cur = 0; e->n_cur = 0; e->cur_base = 0; e->next_base = 0; e->level = 0; e->level_open = false;
+    e->collected.clear();
     return 0;
 }
 
@@ -444,6 +458,7 @@ int vsr_bfs(const VsrModel* m, const VsrRunOpts* opts, VsrStats* stats, void* tr
         if (opts->verbose) fprintf(stderr, "vsr_bfs: %s\n", err);
         return rc;
     }
+    const double t_setup = now_s() - t0;
     rc = vsr_engine_seed_init(e);
     VsrLevelInfo li;
     if (!rc) rc = vsr_engine_finish_level(e, &li);
@@ -479,6 +494,7 @@ int vsr_bfs(const VsrModel* m, const VsrRunOpts* opts, VsrStats* stats, void* tr
         s.trace_len = n > 0 ? n : 0;
     }
     s.seconds_total = now_s() - t0;
+    s.seconds_setup = t_setup;
     *stats = s;
     if (rc && opts->verbose) fprintf(stderr, "vsr_bfs: %s\n", e->last_error);
     vsr_engine_destroy(e);

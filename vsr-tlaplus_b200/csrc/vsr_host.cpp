@@ -698,6 +698,16 @@ int vsr_successors(const VsrModel* m, const void* state, void* out, size_t cap, 
     return n;
 }
 
+int vsr_enabled_candidates(const VsrModel* m, const void* state, uint32_t* out, size_t cap) {
+    int n = 0;
+    for (int c = 0; c < m->ops->ncand; c++) {
+        if (!m->ops->guard(&m->run, (const uint32_t*)state, c)) continue;
+        if ((size_t)n < cap) out[n] = (uint32_t)c;
+        n++;
+    }
+    return n;
+}
+
 int vsr_canon(const VsrModel* m, void* s) { return m->run.symmetry ? m->ops->canon((uint32_t*)s) : 0; }
 uint64_t vsr_fingerprint(const VsrModel* m, const void* s) { return m->ops->fingerprint((const uint32_t*)s, m->run.use_view); }
 uint32_t vsr_aux_key(const VsrModel* m, const void* s) { return m->ops->aux_key((const uint32_t*)s); }
