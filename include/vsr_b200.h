@@ -75,6 +75,8 @@ int vsr_successors(const VsrModel* m, const void* state, void* out, size_t cap, 
 int vsr_enabled_candidates(const VsrModel* m, const void* state, uint32_t* out, size_t cap);
 int vsr_canon(const VsrModel* m, void* state);                           /* SYMMETRY representative, VSR.tla:151 */
 uint64_t vsr_fingerprint(const VsrModel* m, const void* state);          /* FP64 of the VIEW projection, VSR.tla:149-150 */
+/* the same fingerprint by its byte-at-a-time definition (vsr_fingerprint and the GPU use the slicing-by-8 form) */
+uint64_t vsr_fingerprint_bytewise(const VsrModel* m, const void* state);
 uint32_t vsr_aux_key(const VsrModel* m, const void* state);
 int vsr_invariant(const VsrModel* m, const void* state);                 /* 0 = all hold, else mask bit of the violated one; VSR.tla:926-952 */
 int vsr_unpack(const VsrModel* m, const void* state, VsrFlatState* out);

@@ -180,3 +180,21 @@ def test_view_masks_aux_variables_out_of_the_fingerprint(pkg):
     assert mc.fingerprint(t) == mc.fingerprint(s)
     assert nv.fingerprint(t) != nv.fingerprint(s)
     assert mc.aux_key(t) != mc.aux_key(s)
+
+
+def test_sliced_fingerprint_equals_bytewise_definition(pkg):
+    """vsr_fingerprint (slicing-by-8, what the GPU computes) == the byte-at-a-time FP64 definition, on real states,
+    with and without VIEW, for layouts with an even and an odd number of VIEW words"""
+    import random
+    for (R, V, L, view) in [(3, 2, 2, True), (3, 2, 2, False), (3, 3, 3, True), (5, 2, 2, True), (2, 1, 1, True), (2, 2, 2, True)]:
+        mc = pkg.ModelChecker.from_constants(R, V, L, view=view)
+        rnd = random.Random(R * 100 + V * 10 + L)
+        s = mc.init_state()
+        for _ in range(300):
+            buf = (C.c_uint8 * mc.state_bytes).from_buffer_copy(s)
+            assert mc._lib.vsr_fingerprint(mc._h, buf) == mc._lib.vsr_fingerprint_bytewise(mc._h, buf)
+            succ = mc.successors(s)
+            if not succ:
+                s = mc.init_state()
+                continue
+            s = rnd.choice(succ)[0]

@@ -96,12 +96,30 @@ template <class L> struct Ops {
     }
 
     /* ---------------------------------------------------------------- the step function */
+    /* candidate groups: the blocks of the cascade below, in Next's textual order */
+    static constexpr int NGRP = 13;
+    static VSR_HD int grp_begin(int g) {
+        const int b[NGRP + 1] = {L::C_TIMER, L::C_HSVC, L::C_SDVC, L::C_HDVC, L::C_SSV, L::C_RSV, L::C_CREQ, L::C_RPREP,
+                                 L::C_RPOK, L::C_EXEC, L::C_SGS, L::C_RGS, L::C_RNS, L::NCAND};
+        return b[g];
+    }
     template <bool APPLY> static VSR_HD int step(const RunCfg& run, const uint32_t* s, int cand, uint32_t* n) {
+        return cand < L::C_HSVC ? step_grp<APPLY, 0>(run, s, cand, n) : cand < L::C_SDVC ? step_grp<APPLY, 1>(run, s, cand, n)
+             : cand < L::C_HDVC ? step_grp<APPLY, 2>(run, s, cand, n) : cand < L::C_SSV ? step_grp<APPLY, 3>(run, s, cand, n)
+             : cand < L::C_RSV ? step_grp<APPLY, 4>(run, s, cand, n) : cand < L::C_CREQ ? step_grp<APPLY, 5>(run, s, cand, n)
+             : cand < L::C_RPREP ? step_grp<APPLY, 6>(run, s, cand, n) : cand < L::C_RPOK ? step_grp<APPLY, 7>(run, s, cand, n)
+             : cand < L::C_EXEC ? step_grp<APPLY, 8>(run, s, cand, n) : cand < L::C_SGS ? step_grp<APPLY, 9>(run, s, cand, n)
+             : cand < L::C_RGS ? step_grp<APPLY, 10>(run, s, cand, n) : cand < L::C_RNS ? step_grp<APPLY, 11>(run, s, cand, n)
+             : step_grp<APPLY, 12>(run, s, cand, n);
+    }
+    /* one group's guard (+ effect when APPLY): only this group's code is instantiated, so the device can scan a
+       group's candidates in a tight loop */
+    template <bool APPLY, int GRP> static VSR_HD int step_grp(const RunCfg& run, const uint32_t* s, int cand, uint32_t* n) {
         if (APPLY) {
             for (int i = 0; i < L::NW; i++) n[i] = s[i];
         }
         /* ---- TimerSendSVC, VSR.tla:578-590 */
-        if (cand < L::C_HSVC) {
+        if constexpr (GRP == 0) {
             const int r = cand - L::C_TIMER;
             const int aux = (int)VGET(L, AUX_SVC, s, 0);
             if (!(aux < L::L)) return 0;
@@ -118,7 +136,7 @@ template <class L> struct Ops {
             return e ? e : 1;
         }
         /* ---- ReceiveHigherSVC :602-613 / ReceiveMatchingSVC :625-634 */
-        if (cand < L::C_SDVC) {
+        if constexpr (GRP == 1) {
             const bool higher = cand < L::C_MSVC;
             const int idx = cand - (higher ? L::C_HSVC : L::C_MSVC);
             if (VGET(L, SVC_ST, s, idx) != ST_PENDING) return 0; /* ReceivableMsg :272-275 */
@@ -146,7 +164,7 @@ template <class L> struct Ops {
             }
         }
         /* ---- SendDVC :648-669 */
-        if (cand < L::C_HDVC) {
+        if constexpr (GRP == 2) {
             const int r = cand - L::C_SDVC;
             if (VGET(L, STATUS, s, r) != 1) return 0;
             if (VGET(L, SENT_DVC, s, r) != 0) return 0;
@@ -173,7 +191,7 @@ template <class L> struct Ops {
             return 1;
         }
         /* ---- ReceiveHigherDVC :677-688 / ReceiveMatchingDVC :696-703 */
-        if (cand < L::C_SSV) {
+        if constexpr (GRP == 3) {
             const bool higher = cand < L::C_MDVC;
             const int idx = cand - (higher ? L::C_HDVC : L::C_MDVC);
             if (VGET(L, DVC_ST, s, idx) != ST_PENDING) return 0;
@@ -201,7 +219,7 @@ template <class L> struct Ops {
             }
         }
         /* ---- SendSV :735-760 with HighestLog/HighestOpNumber/HighestCommitNumber :716-733 */
-        if (cand < L::C_RSV) {
+        if constexpr (GRP == 4) {
             const int r = cand - L::C_SSV;
             if (VGET(L, STATUS, s, r) != 1) return 0;
             if (VGET(L, SENT_SV, s, r) != 0) return 0;
@@ -248,7 +266,7 @@ template <class L> struct Ops {
             return 1;
         }
         /* ---- ReceiveSV :773-793 */
-        if (cand < L::C_CREQ) {
+        if constexpr (GRP == 5) {
             const int idx = cand - L::C_RSV;
             if (VGET(L, SV_ST, s, idx) != ST_PENDING) return 0;
             const int v = idx / O + 2;
@@ -274,7 +292,7 @@ template <class L> struct Ops {
             return 1;
         }
         /* ---- ReceiveClientRequest :366-394 */
-        if (cand < L::C_RPREP) {
+        if constexpr (GRP == 6) {
             const int r = (cand - L::C_CREQ) / V, vi = (cand - L::C_CREQ) % V;
             const int v = (int)VGET(L, VIEWN, s, r);
             if (primary(v) != r) return 0;
@@ -332,7 +350,7 @@ template <class L> struct Ops {
             return mult;
         }
         /* ---- ReceivePrepareMsg :405-428 */
-        if (cand < L::C_RPOK) {
+        if constexpr (GRP == 7) {
             const int x = (cand - L::C_RPREP) / O, dp = (cand - L::C_RPREP) % O;
             const int pv = (int)VGET(L, PR_VIEW, s, x);
             if (pv == 0) return 0;
@@ -357,7 +375,7 @@ template <class L> struct Ops {
             return 1;
         }
         /* ---- ReceivePrepareOkMsg :437-447 */
-        if (cand < L::C_EXEC) {
+        if constexpr (GRP == 8) {
             const int idx = cand - L::C_RPOK;
             if (VGET(L, POK_ST, s, idx) != ST_PENDING) return 0;
             const int sp = idx % O, nn = (idx / O) % V + 1, v = idx / (O * V) + 1;
@@ -372,7 +390,7 @@ template <class L> struct Ops {
             return 1;
         }
         /* ---- ExecuteOp :462-476, IsCommitted :457-460 */
-        if (cand < L::C_SGS) {
+        if constexpr (GRP == 9) {
             const int r = cand - L::C_EXEC;
             if (primary((int)VGET(L, VIEWN, s, r)) != r) return 0;
             if (VGET(L, STATUS, s, r) != 0) return 0;
@@ -389,7 +407,7 @@ template <class L> struct Ops {
             return 1;
         }
         /* ---- SendGetState :496-516 */
-        if (cand < L::C_RGS) {
+        if constexpr (GRP == 10) {
             const int c = cand - L::C_SGS;
             const int j = c % O, dp = (c / O) % O, x = c / (O * O);
             const int pv = (int)VGET(L, PR_VIEW, s, x);
@@ -423,7 +441,7 @@ template <class L> struct Ops {
             return 1;
         }
         /* ---- ReceiveGetState :526-543 */
-        if (cand < L::C_RNS) {
+        if constexpr (GRP == 11) {
             const int gi = cand - L::C_RGS;
             if (VGET(L, GS_ST, s, gi) != ST_PENDING) return 0;
             const int v = gi / O + 2;
@@ -442,7 +460,7 @@ template <class L> struct Ops {
             return 1;
         }
         /* ---- ReceiveNewState :551-567 */
-        {
+        if constexpr (GRP == 12) {
             const int gi = cand - L::C_RNS;
             if (VGET(L, NS_ST, s, gi) != ST_PENDING) return 0;
             const int v = gi / O + 2;
@@ -456,6 +474,7 @@ template <class L> struct Ops {
             VSET(L, NS_ST, n, gi, ST_CONSUMED);
             return 1;
         }
+        return 0;
     }
 
     /* action id (VSR_ACT_*, = textual position in Next) of a candidate index */
@@ -608,6 +627,7 @@ inline void fp64_build_table(uint64_t tab[256]) {
 }
 
 template <class L> VSR_HD uint64_t fp64_view(const uint64_t* __restrict__ tab, const uint32_t* w, bool use_view) {
+    /* byte-at-a-time form (the definition) */
     uint64_t fp = FP64_POLY;
     constexpr int full = L::VIEW_BITS >> 5, rem = L::VIEW_BITS & 31;
     const int nw = use_view ? (full + (rem ? 1 : 0)) : L::NW;
@@ -618,6 +638,43 @@ template <class L> VSR_HD uint64_t fp64_view(const uint64_t* __restrict__ tab, c
             fp = (fp >> 8) ^ tab[(x ^ (uint32_t)fp) & 0xFF];
             x >>= 8;
         }
+    }
+    return fp;
+}
+
+/* Slicing-by-8: the same function eight bytes per step.  S[j][b] = state after byte b followed by j zero bytes,
+   so fp' = S7[y0] ^ S6[y1] ^ ... ^ S0[y7] with y = fp ^ (next 8 bytes, little-endian).  The eight lookups of a
+   step are independent (the byte form is a chain of 4*NW dependent shared-memory loads). */
+inline void fp64_build_slices(uint64_t s8[8 * 256]) {
+    fp64_build_table(s8);
+    for (int j = 1; j < 8; j++)
+        for (int b = 0; b < 256; b++) {
+            const uint64_t p = s8[(j - 1) * 256 + b];
+            s8[j * 256 + b] = (p >> 8) ^ s8[p & 0xFF];
+        }
+}
+
+template <class L> VSR_HD uint64_t fp64_view8(const uint64_t* __restrict__ s8, const uint32_t* w, bool use_view) {
+    static_assert(L::NW % 2 == 0, "whole 64-bit words");
+    uint64_t fp = FP64_POLY;
+    constexpr int full = L::VIEW_BITS >> 5, rem = L::VIEW_BITS & 31;
+    /* bytes of whole zero words after the VIEW prefix are not hashed by the byte form either: hash ceil(nw/2) pairs,
+       but an odd word count must not pull in the next word: mask it to zero and stop the byte count there */
+    const int nw = use_view ? (full + (rem ? 1 : 0)) : L::NW;
+    int i = 0;
+    for (; i + 1 < nw; i += 2) {
+        uint32_t lo = w[i], hi = w[i + 1];
+        if (use_view && i + 1 == full) hi &= (1u << rem) - 1u;
+        const uint64_t y = fp ^ (((uint64_t)hi << 32) | lo);
+        fp = s8[7 * 256 + (y & 0xFF)] ^ s8[6 * 256 + ((y >> 8) & 0xFF)] ^ s8[5 * 256 + ((y >> 16) & 0xFF)] ^
+             s8[4 * 256 + ((y >> 24) & 0xFF)] ^ s8[3 * 256 + ((y >> 32) & 0xFF)] ^ s8[2 * 256 + ((y >> 40) & 0xFF)] ^
+             s8[1 * 256 + ((y >> 48) & 0xFF)] ^ s8[(y >> 56) & 0xFF];
+    }
+    if (i < nw) { /* one trailing 32-bit word: four bytes */
+        uint32_t x = w[i];
+        if (use_view && i == full) x &= (1u << rem) - 1u;
+        const uint32_t y = x ^ (uint32_t)fp;
+        fp = (fp >> 32) ^ s8[3 * 256 + (y & 0xFF)] ^ s8[2 * 256 + ((y >> 8) & 0xFF)] ^ s8[1 * 256 + ((y >> 16) & 0xFF)] ^ s8[(y >> 24) & 0xFF];
     }
     return fp;
 }

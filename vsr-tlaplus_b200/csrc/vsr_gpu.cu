@@ -20,6 +20,7 @@ namespace vsr {
 struct GpuOps {
     int R, V, K, nw, bytes, rec_bytes;
     size_t expand_smem;
+    int states_per_block;
     cudaError_t (*launch_expand)(const ExpandParams&, int grid, cudaStream_t);
     cudaError_t (*launch_insert)(const InsertParams&, cudaStream_t);
     cudaError_t (*prepare)(int* blocks_per_sm);
@@ -27,12 +28,12 @@ struct GpuOps {
 
 template <class L> struct GpuThunks {
     static cudaError_t prepare(int* blocks_per_sm) {
-        cudaError_t e = cudaFuncSetAttribute(expand_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlockSmem<L>));
+        cudaError_t e = cudaFuncSetAttribute(expand_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(typename ExpandCfg<L>::Smem));
         if (e != cudaSuccess) return e;
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, expand_kernel<L>, EXP_WARPS * 32, sizeof(BlockSmem<L>));
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, expand_kernel<L>, ExpandCfg<L>::WARPS * 32, sizeof(typename ExpandCfg<L>::Smem));
     }
     static cudaError_t launch_expand(const ExpandParams& p, int grid, cudaStream_t st) {
-        expand_kernel<L><<<grid, EXP_WARPS * 32, sizeof(BlockSmem<L>), st>>>(p);
+        expand_kernel<L><<<grid, ExpandCfg<L>::WARPS * 32, sizeof(typename ExpandCfg<L>::Smem), st>>>(p);
         return cudaGetLastError();
     }
     static cudaError_t launch_insert(const InsertParams& q, cudaStream_t st) {
@@ -42,7 +43,7 @@ template <class L> struct GpuThunks {
         return cudaGetLastError();
     }
     static const GpuOps* get() {
-        static const GpuOps ops = {L::R, L::V, L::K, L::NW, L::BYTES, (int)(L::BYTES + sizeof(RecHdr)), sizeof(BlockSmem<L>),
+        static const GpuOps ops = {L::R, L::V, L::K, L::NW, L::BYTES, (int)(L::BYTES + sizeof(RecHdr)), sizeof(typename ExpandCfg<L>::Smem), ExpandCfg<L>::WARPS * 32,
                                    launch_expand, launch_insert, prepare};
         return &ops;
     }
@@ -207,14 +208,14 @@ int vsr_engine_create(const VsrModel* m, const VsrRunOpts* opts, int rank, int w
     if (e->trace_cap && (ce = cudaMalloc(&e->trace, e->trace_cap * 8)) != cudaSuccess) return bail("cudaMalloc(trace)", ce);
     if ((ce = cudaMalloc(&e->ctr, sizeof(DevCounters))) != cudaSuccess) return bail("cudaMalloc", ce);
     if ((ce = cudaMalloc(&e->ties, e->tie_cap * sizeof(TieRec))) != cudaSuccess) return bail("cudaMalloc", ce);
-    if ((ce = cudaMalloc(&e->fp_tab, 256 * 8)) != cudaSuccess) return bail("cudaMalloc", ce);
+    if ((ce = cudaMalloc(&e->fp_tab, 8 * 256 * 8)) != cudaSuccess) return bail("cudaMalloc", ce);
     if ((ce = cudaMalloc(&e->init_rec, e->g->rec_bytes)) != cudaSuccess) return bail("cudaMalloc", ce);
-    if ((ce = cudaMemcpyAsync(e->fp_tab, fp64_table(), 256 * 8, cudaMemcpyHostToDevice, e->stream)) != cudaSuccess) return bail("memcpy", ce);
+    if ((ce = cudaMemcpyAsync(e->fp_tab, fp64_table(), 8 * 256 * 8, cudaMemcpyHostToDevice, e->stream)) != cudaSuccess) return bail("memcpy", ce);
     e->st.table_capacity = tcap;
     e->st.frontier_capacity = fcap;
     e->st.bytes_table = tcap * 16;
     e->st.bytes_frontier = 2 * fcap * S;
-    e->st.bytes_h2d += 256 * 8;
+    e->st.bytes_h2d += 8 * 256 * 8;
     if ((ce = cudaStreamSynchronize(e->stream)) != cudaSuccess) return bail("sync", ce);
     *out = e;
     return 0;
@@ -287,8 +288,7 @@ int vsr_engine_expand(VsrEngine* e) {
     if (e->n_cur == 0) return 0;
     ExpandParams p;
     fill_params(e, p);
-    const uint64_t chunks = (e->n_cur + 31) / 32;
-    uint64_t want_blocks = (chunks + EXP_WARPS - 1) / EXP_WARPS;
+    const uint64_t want_blocks = (e->n_cur + e->g->states_per_block - 1) / e->g->states_per_block;
     const uint64_t max_blocks = (uint64_t)e->sms * e->blocks_per_sm; /* persistent: whole multiples of the SM count */
     int grid = (int)(want_blocks < max_blocks ? want_blocks : max_blocks);
     if (grid < 1) grid = 1;

@@ -74,7 +74,7 @@ struct ExpandParams {
     DevCounters* ctr;
     TieRec* ties;
     unsigned long long tie_cap;
-    const uint64_t* fp_tab;      /* 256-entry FP64 byte table */
+    const uint64_t* fp_tab;      /* 8 x 256 FP64 slicing tables */
     RunCfg run;
     int level;                   /* depth of the states being GENERATED (Init = 1) */
     int check_deadlock;
@@ -174,37 +174,59 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_
 
 /* ------------------------------------------------------------------ expand kernel */
 
-constexpr int EXP_WARPS = 8; /* warps per block */
-constexpr int QCAP = 64;     /* (lane, candidate) queue per warp */
-constexpr int SCAP = 64;     /* staged new states per warp */
+constexpr int SCAP = 64;      /* staged new states per warp */
+constexpr int QG = 512;       /* queue entries per action group per block round */
 
-template <class L> struct WarpSmem {
-    uint32_t par[32 * (L::NW + 1)];              /* this warp's 32 parent states, row stride NW+1 (bank-conflict-free) */
+template <class L> struct WarpStage {
     alignas(16) uint32_t stage[SCAP * L::NW];    /* new states, packed back to back for the bulk store */
     unsigned long long tstage[SCAP];             /* their trace records */
-    uint32_t queue[QCAP];
 };
-template <class L> struct BlockSmem {
-    uint64_t fp_tab[256];
-    WarpSmem<L> w[EXP_WARPS];
+template <class L, int WARPS> struct BlockSmemT {
+    static constexpr int NS = WARPS * 32;        /* parent states per block round: one per thread */
+    static constexpr int NG = 13;                /* action groups (Ops<L>::NGRP) */
+    uint64_t fp_tab[8 * 256];                    /* FP64 slicing-by-8 tables */
+    uint32_t par[NS * (L::NW + 1)];              /* parents, row stride NW+1 (odd: bank-conflict-free column reads) */
+    uint16_t queue[NG][QG];                      /* enabled (state, candidate) pairs, one queue per action group */
+    int qcount[NG];
+    int take;
+    unsigned long long round_first;
+    WarpStage<L> w[WARPS];
+};
+/* warps per block: as many as fit twice per SM (2 x <= 113 KB of shared memory) */
+template <class L> struct ExpandCfg {
+    static constexpr int WARPS = sizeof(BlockSmemT<L, 16>) <= 113 * 1024 ? 16 : (sizeof(BlockSmemT<L, 12>) <= 113 * 1024 ? 12 : 8);
+    typedef BlockSmemT<L, WARPS> Smem;
 };
 
+/*
+ * Block-synchronous scan, action-pure apply.  A block takes NS = 32*WARPS frontier states (one per thread):
+ *   scan   all warps walk Next's action groups in textual order together; each thread evaluates every guard on its
+ *          own state and pushes enabled (state, candidate) pairs to that GROUP's queue (one shared-memory atomic per
+ *          warp ballot).  Everybody runs the same few kB of guard code at the same time.
+ *   apply  after one barrier, warps take batches of 32 pairs of ONE group and apply them one per lane: no
+ *          divergence between actions inside a warp, full lanes except one partial batch per group.
+ * (The first version let every warp walk guards and effects on its own: 88 kB of SASS against a 32 kB instruction
+ * cache gave 55 % `no_instruction` stall samples.  A version with a barrier per group starved on barriers instead.)
+ */
 template <class L> struct Expander {
     typedef Ops<L> O_;
+    typedef typename ExpandCfg<L>::Smem Smem;
+    static constexpr int WARPS = ExpandCfg<L>::WARPS, NS = Smem::NS;
     const ExpandParams& P;
-    WarpSmem<L>& S;
-    const uint64_t* tab;
-    const int lane;
-    int qn = 0, sn = 0;
+    Smem& B;
+    WarpStage<L>& S;
+    const int lane, warp, tid;
+    int sn = 0;
     unsigned long long gen = 0;
     unsigned probes = 0, coll = 0, ties = 0;
-    unsigned long long chunk_first = 0; /* index in P.in of lane 0's parent */
+    const uint32_t* mine = nullptr;
+    bool have = false, any = false;
 
-    __device__ Expander(const ExpandParams& p, WarpSmem<L>& s, const uint64_t* t, int ln) : P(p), S(s), tab(t), lane(ln) {}
+    __device__ Expander(const ExpandParams& p, Smem& b) : P(p), B(b), S(b.w[threadIdx.x >> 5]), lane(threadIdx.x & 31), warp(threadIdx.x >> 5), tid(threadIdx.x) {}
 
     /* flush the first n staged states (n <= 32) to the next frontier: one atomicAdd for the block of
        ids, one TMA bulk store for the states, then move the remainder (< 32 states) down */
-    __device__ void flush(int n) {
+    __device__ __noinline__ void flush(int n) {
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(&P.ctr->out_count, (unsigned long long)n);
         base = __shfl_sync(0xffffffffu, base, 0);
@@ -239,30 +261,25 @@ template <class L> struct Expander {
         __syncwarp();
     }
 
-    /* apply the first k queued (lane, candidate) pairs, one per lane */
-    __device__ void drain(int k) {
-        uint32_t n[L::NW];
+    /* fingerprint, route, insert, stage: the part of apply that does not depend on the action */
+    __device__ __noinline__ void emit(const uint32_t* n, int mult, int cand, int si, bool act) {
         bool isnew = false;
         int bad = 0;
         unsigned long long trec = 0;
-        if (lane < k) {
-            const uint32_t item = S.queue[lane];
-            const int pl = item & 31, cand = item >> 5;
-            const uint32_t* parent = &S.par[pl * (L::NW + 1)];
-            const int mult = O_::template step<true>(P.run, parent, cand, n);
+        if (act) {
             if (mult < 0) {
                 atomicCAS(&P.ctr->error, 0, mult);
             } else if (mult > 0) {
-                gen += (unsigned long long)mult;
-                uint64_t fp = fp64_view<L>(tab, n, P.run.use_view != 0);
+                uint64_t fp = fp64_view8<L>(B.fp_tab, n, P.run.use_view != 0);
                 if (fp == 0) fp = 1;
                 const uint32_t chk = check_hash<L>(n, P.run.use_view != 0);
                 const uint32_t auxkey = O_::aux_key(n);
                 const uint64_t meta = make_meta(P.level, auxkey, chk);
-                const uint64_t parent_gid = make_gid(P.rank, P.in_base + chunk_first + pl);
+                const uint64_t parent_gid = make_gid(P.rank, P.in_base + B.round_first + si);
                 trec = make_trec(parent_gid, (uint32_t)cand);
                 const int owner = P.world > 1 ? (int)(fp >> P.owner_shift) : P.rank;
                 if (owner == P.rank) {
+                    gen += (unsigned long long)mult; /* successors sent to a peer are counted where they are inserted */
                     const int r = table_insert(P.table, P.table_mask, fp, meta, probes, coll);
                     isnew = r == INS_NEW;
                     if (isnew) bad = O_::invariant(P.run, n);
@@ -301,46 +318,87 @@ template <class L> struct Expander {
         sn += __popc(newmask);
         __syncwarp();
         while (sn >= 32) flush(32);
-        /* shift the queue */
-        const int rest = qn - k;
-        uint32_t q = 0;
-        if (lane < rest) q = S.queue[k + lane];
-        __syncwarp();
-        if (lane < rest) S.queue[lane] = q;
-        qn = rest;
-        __syncwarp();
     }
 
-    __device__ void run_chunk(unsigned long long first, int count) {
-        chunk_first = first;
-        /* coalesced load of `count` parent states into padded rows */
-        const uint32_t* src = P.in + first * L::NW;
-        for (int i = lane; i < count * L::NW; i += 32) S.par[(i / L::NW) * (L::NW + 1) + (i % L::NW)] = __ldg(src + i);
-        __syncwarp();
-        uint32_t mine[L::NW];
-        const bool have = lane < count;
-        if (have) {
-            for (int j = 0; j < L::NW; j++) mine[j] = S.par[lane * (L::NW + 1) + j];
-        } else {
-            for (int j = 0; j < L::NW; j++) mine[j] = 0;
-        }
-        bool any = false;
-        for (int cand = 0; cand < L::NCAND; cand++) {
+    /* scan one action group: guards only */
+    template <int G> __device__ __forceinline__ void scan() {
+        const int c0 = O_::grp_begin(G), c1 = O_::grp_begin(G + 1);
+#pragma unroll 1
+        for (int cand = c0; cand < c1; cand++) {
             int m = 0;
-            if (have) m = O_::template step<false>(P.run, mine, cand, nullptr);
+            if (have) m = O_::template step_grp<false, G>(P.run, mine, cand, nullptr);
             const unsigned en = __ballot_sync(0xffffffffu, m > 0);
             if (en) {
-                if (m > 0) {
-                    any = true;
-                    S.queue[qn + __popc(en & ((1u << lane) - 1u))] = (uint32_t)lane | ((uint32_t)cand << 5);
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&B.qcount[G], __popc(en));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (m > 0) any = true;
+                /* positions below QG are queued; the rest (queue full) are applied right here by their own lanes.
+                   The counter only grows, so a position is either queued by exactly one lane or nobody's. */
+                const int pos = base + __popc(en & ((1u << lane) - 1u));
+                const bool inl = m > 0 && pos >= QG;
+                if (m > 0 && !inl) B.queue[G][pos] = (uint16_t)(tid | ((cand - c0) << 9));
+                if (__any_sync(0xffffffffu, inl)) {
+                    uint32_t n[L::NW];
+                    int mult = 0;
+                    if (inl) mult = O_::template step_grp<true, G>(P.run, mine, cand, n);
+                    emit(n, mult, cand, tid, inl);
                 }
-                qn += __popc(en);
-                __syncwarp();
-                if (qn >= 32) drain(32);
             }
         }
-        if (qn > 0) drain(qn);
-        if (P.check_deadlock && have && !any) atomicMin(&P.ctr->dead_id, P.in_base + first + lane);
+    }
+    /* apply one batch of <= 32 pairs of group G */
+    template <int G> __device__ __noinline__ void apply(int b, int k) {
+        uint32_t n[L::NW];
+        int mult = 0, cand = 0, si = 0;
+        const bool act = lane < k;
+        if (act) {
+            const unsigned item = B.queue[G][b + lane];
+            si = item & 511;
+            cand = O_::grp_begin(G) + (int)(item >> 9);
+            mult = O_::template step_grp<true, G>(P.run, &B.par[si * (L::NW + 1)], cand, n);
+        }
+        emit(n, mult, cand, si, act);
+    }
+
+    __device__ void run_round(unsigned long long first, int count) {
+        /* coalesced load of `count` parent states into padded rows */
+        const uint32_t* src = P.in + first * L::NW;
+        for (int i = tid; i < count * L::NW; i += NS) B.par[(i / L::NW) * (L::NW + 1) + (i % L::NW)] = __ldg(src + i);
+        if (tid < Smem::NG) B.qcount[tid] = 0;
+        if (tid == 0) { B.round_first = first; B.take = 0; }
+        __syncthreads();
+        have = tid < count;
+        mine = &B.par[(have ? tid : 0) * (L::NW + 1)];
+        any = false;
+        scan<0>(); scan<1>(); scan<2>(); scan<3>(); scan<4>(); scan<5>(); scan<6>();
+        scan<7>(); scan<8>(); scan<9>(); scan<10>(); scan<11>(); scan<12>();
+        if (P.check_deadlock && have && !any) atomicMin(&P.ctr->dead_id, P.in_base + first + tid);
+        __syncthreads();
+        /* batches: group g has ceil(min(count_g, QG) / 32) of them */
+        int nb[Smem::NG], total = 0;
+        for (int g = 0; g < Smem::NG; g++) {
+            const int c = B.qcount[g] < QG ? B.qcount[g] : QG;
+            nb[g] = (c + 31) >> 5;
+            total += nb[g];
+        }
+        for (;;) {
+            int t = 0;
+            if (lane == 0) t = atomicAdd(&B.take, 1);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            if (t >= total) break;
+            int g = 0;
+            while (t >= nb[g]) { t -= nb[g]; g++; }
+            const int c = B.qcount[g] < QG ? B.qcount[g] : QG;
+            const int b = t * 32, k = c - b < 32 ? c - b : 32;
+            switch (g) {
+            case 0: apply<0>(b, k); break;   case 1: apply<1>(b, k); break;   case 2: apply<2>(b, k); break;
+            case 3: apply<3>(b, k); break;   case 4: apply<4>(b, k); break;   case 5: apply<5>(b, k); break;
+            case 6: apply<6>(b, k); break;   case 7: apply<7>(b, k); break;   case 8: apply<8>(b, k); break;
+            case 9: apply<9>(b, k); break;   case 10: apply<10>(b, k); break; case 11: apply<11>(b, k); break;
+            default: apply<12>(b, k); break;
+            }
+        }
     }
 
     __device__ void finish() {
@@ -361,22 +419,23 @@ template <class L> struct Expander {
     }
 };
 
-template <class L> __global__ void __launch_bounds__(EXP_WARPS * 32) expand_kernel(const ExpandParams P) {
+template <class L> __global__ void __launch_bounds__(ExpandCfg<L>::WARPS * 32, 2) expand_kernel(const ExpandParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    BlockSmem<L>& B = *reinterpret_cast<BlockSmem<L>*>(smem_raw);
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) B.fp_tab[i] = P.fp_tab[i];
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    Expander<L> X(P, B.w[warp], B.fp_tab, lane);
-    const unsigned long long nchunks = (P.n_in + 31) / 32;
+    typedef typename ExpandCfg<L>::Smem Smem;
+    Smem& B = *reinterpret_cast<Smem*>(smem_raw);
+    for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) B.fp_tab[i] = P.fp_tab[i];
+    __shared__ unsigned long long next_round;
+    Expander<L> X(P, B);
+    const unsigned long long nrounds = (P.n_in + Smem::NS - 1) / Smem::NS;
     for (;;) {
-        unsigned long long c = 0;
-        if (lane == 0) c = atomicAdd(&P.ctr->work_next, 1ull);
-        c = __shfl_sync(0xffffffffu, c, 0);
-        if (c >= nchunks) break;
-        const unsigned long long first = c * 32;
-        const int count = (int)((P.n_in - first) < 32 ? (P.n_in - first) : 32);
-        X.run_chunk(first, count);
+        __syncthreads();
+        if (threadIdx.x == 0) next_round = atomicAdd(&P.ctr->work_next, 1ull);
+        __syncthreads();
+        const unsigned long long c = next_round;
+        if (c >= nrounds) break;
+        const unsigned long long first = c * Smem::NS;
+        const int count = (int)((P.n_in - first) < (unsigned long long)Smem::NS ? (P.n_in - first) : Smem::NS);
+        X.run_round(first, count);
     }
     X.finish();
 }
@@ -392,15 +451,16 @@ template <class L> __global__ void __launch_bounds__(256) insert_kernel(const In
     const uint8_t* rec = Q.recs + (have ? i : 0) * (L::BYTES + sizeof(RecHdr));
     const uint32_t* n = (const uint32_t*)rec;
     const RecHdr* h = (const RecHdr*)(rec + L::BYTES);
-    unsigned probes = 0, coll = 0;
+    unsigned probes = 0, coll = 0, nties = 0;
+    unsigned long long gen = 0;
     if (have) {
         /* meta == 0: the sender (host seeding Init) left tag computation to the device */
         const uint64_t meta = h->meta ? h->meta : make_meta(P.level, Ops<L>::aux_key(n), check_hash<L>(n, P.run.use_view != 0));
         const int r = table_insert(P.table, P.table_mask, h->fp, meta, probes, coll);
         isnew = r == INS_NEW;
-        atomicAdd(&P.ctr->generated, (unsigned long long)h->mult);
+        gen = h->mult;
         if (r == INS_TIE) {
-            atomicAdd(&P.ctr->ties, 1ull);
+            nties = 1;
             const unsigned long long t = atomicAdd(&P.ctr->tie_count, 1ull);
             if (t < P.tie_cap) {
                 TieRec tr;
@@ -409,8 +469,19 @@ template <class L> __global__ void __launch_bounds__(256) insert_kernel(const In
                 P.ties[t] = tr;
             } else atomicExch(&P.ctr->overflow, 2);
         }
+    }
+    /* per-warp totals: one atomic per counter per warp, not per record */
+    for (int o = 16; o; o >>= 1) {
+        gen += __shfl_xor_sync(0xffffffffu, gen, o);
+        probes += __shfl_xor_sync(0xffffffffu, probes, o);
+        coll += __shfl_xor_sync(0xffffffffu, coll, o);
+        nties += __shfl_xor_sync(0xffffffffu, nties, o);
+    }
+    if (lane == 0) {
+        if (gen) atomicAdd(&P.ctr->generated, gen);
+        if (probes) atomicAdd(&P.ctr->probes, (unsigned long long)probes);
         if (coll) atomicAdd(&P.ctr->collisions, (unsigned long long)coll);
-        atomicAdd(&P.ctr->probes, (unsigned long long)probes);
+        if (nties) atomicAdd(&P.ctr->ties, (unsigned long long)nties);
     }
     const unsigned newmask = __ballot_sync(0xffffffffu, isnew);
     if (newmask) {

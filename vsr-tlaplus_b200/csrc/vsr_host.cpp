@@ -28,7 +28,8 @@ template <class L> struct Thunks {
     static int guard(const RunCfg* run, const uint32_t* s, int cand) { return Ops<L>::template step<false>(*run, s, cand, nullptr); }
     static int action_of(int cand) { return Ops<L>::action_of(cand); }
     static int invariant(const RunCfg* run, const uint32_t* w) { return Ops<L>::invariant(*run, w); }
-    static uint64_t fingerprint(const uint32_t* w, int use_view) { return fp64_view<L>(fp64_table(), w, use_view != 0); }
+    static uint64_t fingerprint(const uint32_t* w, int use_view) { return fp64_view8<L>(fp64_table(), w, use_view != 0); }
+    static uint64_t fingerprint_bytewise(const uint32_t* w, int use_view) { return fp64_view<L>(fp64_table(), w, use_view != 0); }
     static uint32_t aux_key(const uint32_t* w) { return Ops<L>::aux_key(w); }
     static int canon(uint32_t* w) { return Ops<L>::canonicalize(w); }
     static int unpack(const uint32_t* w, VsrFlatState* f) { return Conv<L>::unpack(w, f); }
@@ -36,7 +37,7 @@ template <class L> struct Thunks {
     static int literal_cand(const uint32_t* w, int cand) { return Ops<L>::literal_cand(w, cand); }
     static const ModelOps* get() {
         static const ModelOps ops = {L::R, L::V, L::K, L::NW, L::BYTES, L::TOTAL_BITS, L::NCAND, init, step, guard,
-                                     action_of, invariant, fingerprint, aux_key, canon, unpack, pack, literal_cand};
+                                     action_of, invariant, fingerprint, aux_key, canon, unpack, pack, literal_cand, fingerprint_bytewise};
         return &ops;
     }
 };
@@ -50,9 +51,9 @@ const ModelOps* find_model_ops(int R, int V, int K) {
 }
 
 const uint64_t* fp64_table() {
-    static uint64_t tab[256];
+    static uint64_t tab[8 * 256]; /* slicing-by-8 tables; the first 256 entries are the byte table */
     static bool built = false;
-    if (!built) { fp64_build_table(tab); built = true; }
+    if (!built) { fp64_build_slices(tab); built = true; }
     return tab;
 }
 
@@ -710,6 +711,7 @@ int vsr_enabled_candidates(const VsrModel* m, const void* state, uint32_t* out, 
 
 int vsr_canon(const VsrModel* m, void* s) { return m->run.symmetry ? m->ops->canon((uint32_t*)s) : 0; }
 uint64_t vsr_fingerprint(const VsrModel* m, const void* s) { return m->ops->fingerprint((const uint32_t*)s, m->run.use_view); }
+uint64_t vsr_fingerprint_bytewise(const VsrModel* m, const void* s) { return m->ops->fingerprint_bytewise((const uint32_t*)s, m->run.use_view); }
 uint32_t vsr_aux_key(const VsrModel* m, const void* s) { return m->ops->aux_key((const uint32_t*)s); }
 int vsr_invariant(const VsrModel* m, const void* s) { return m->ops->invariant(&m->run, (const uint32_t*)s); }
 int vsr_unpack(const VsrModel* m, const void* s, VsrFlatState* out) { return m->ops->unpack((const uint32_t*)s, out); }

@@ -32,6 +32,7 @@ struct ModelOps {
     int (*unpack)(const uint32_t*, VsrFlatState*);
     int (*pack)(const VsrFlatState*, uint32_t*, int symmetry);
     int (*literal_cand)(const uint32_t*, int cand);
+    uint64_t (*fingerprint_bytewise)(const uint32_t*, int use_view);
 };
 const ModelOps* find_model_ops(int R, int V, int K);
 const GpuOps* find_gpu_ops(int R, int V, int K); /* defined in vsr_gpu.cu */
