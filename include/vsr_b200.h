@@ -167,6 +167,9 @@ int vsr_engine_read_frontier(VsrEngine* e, uint64_t first, uint64_t n, void* hos
 /* trace record of a locally owned state id: parent global id (rank << 48 | local id) and candidate index */
 int vsr_engine_trace_record(VsrEngine* e, uint64_t local_id, uint64_t* parent_out, uint32_t* cand_out);
 int vsr_engine_stats(const VsrEngine* e, VsrStats* out);
+/* membership query: *level_out = BFS depth at which `state` (a canonical packed state) was first seen, 0 if it is not
+ * in this rank's shard of the seen-set; *owner_out = the rank owning its fingerprint */
+int vsr_engine_lookup(VsrEngine* e, const void* state, int* level_out, int* owner_out);
 /* forget everything explored (clears the seen-set, keeps the allocations): ready for seed_init again */
 int vsr_engine_reset(VsrEngine* e);
 const char* vsr_engine_last_error(const VsrEngine* e);

@@ -135,3 +135,26 @@ def test_frontier_overflow_is_loud(pkg):
     mc = pkg.ModelChecker.from_constants(3, 2, 2)
     res = mc.check(max_depth=12, table_capacity=1 << 20, frontier_capacity=256)
     assert res.rc == 152
+
+
+def test_published_behaviour_is_inside_the_explored_set(pkg):
+    """golden cross-check on the README constants (R=3, V=3, L=3): after a BFS to depth 12, the k-th state of the
+    reference's published 24-state counterexample (k <= 12) is in the seen-set, first seen at a depth <= k"""
+    import base64, json, os, zlib
+    from vsr_tlaplus_b200 import dist as vdist
+    mc = pkg.ModelChecker.from_constants(3, 3, 3)
+    eng = vdist.GpuEngine(mc, 0, 1, table_capacity=1 << 22, frontier_capacity=1 << 20)
+    try:
+        res = vdist.ShardedBfs(eng, 0, 1).run(max_depth=12)
+        assert res.rc == 0 and res.depth == 12
+        fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "state_transfer_trace.json")))
+        Flat = pkg.checker.VsrFlatState
+        for k, s in enumerate(fx["states"][:12], start=1):
+            packed = mc.pack(Flat.from_buffer_copy(zlib.decompress(base64.b64decode(s["flat_zlib_b64"]))))
+            lvl, owner = eng.lookup(packed)
+            assert owner == 0 and 0 < lvl <= k, (k, lvl)
+        # and a state that cannot have been reached yet is absent
+        last = mc.pack(Flat.from_buffer_copy(zlib.decompress(base64.b64decode(fx["states"][23]["flat_zlib_b64"]))))
+        assert eng.lookup(last)[0] == 0
+    finally:
+        eng.close()

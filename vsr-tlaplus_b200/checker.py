@@ -128,7 +128,7 @@ EXPORTED_SYMBOLS = [
     "vsr_flat_to_tla", "vsr_action_name", "vsr_action_location", "vsr_bfs", "vsr_engine_create", "vsr_engine_destroy",
     "vsr_engine_record_bytes", "vsr_engine_set_send_buffers", "vsr_engine_seed_init", "vsr_engine_expand",
     "vsr_engine_insert_records", "vsr_engine_finish_level", "vsr_engine_frontier_size", "vsr_engine_read_frontier",
-    "vsr_engine_trace_record", "vsr_engine_stats", "vsr_engine_reset", "vsr_engine_last_error", "vsr_engine_collected", "vsr_engine_build_trace",
+    "vsr_engine_trace_record", "vsr_engine_stats", "vsr_engine_reset", "vsr_engine_lookup", "vsr_engine_last_error", "vsr_engine_collected", "vsr_engine_build_trace",
     "vsr_replay_candidates", "vsr_probe_bench", "vsr_version",
 ]
 
@@ -184,6 +184,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.vsr_engine_trace_record.argtypes = [vp, u64, C.POINTER(u64), C.POINTER(C.c_uint32)]
     lib.vsr_engine_stats.argtypes = [vp, C.POINTER(VsrStats)]
     lib.vsr_engine_reset.argtypes = [vp]
+    lib.vsr_engine_lookup.argtypes = [vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.vsr_engine_last_error.argtypes = [vp]
     lib.vsr_engine_last_error.restype = cp
     lib.vsr_engine_collected.argtypes = [vp, C.c_int, vp, u64]

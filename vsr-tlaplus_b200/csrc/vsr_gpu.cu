@@ -18,6 +18,7 @@
 namespace vsr {
 
 struct GpuOps {
+    uint32_t (*check_hash)(const uint32_t*, int use_view);
     int R, V, K, nw, bytes, rec_bytes;
     size_t expand_smem;
     int states_per_block;
@@ -42,8 +43,9 @@ template <class L> struct GpuThunks {
         insert_kernel<L><<<blocks, 256, 0, st>>>(q);
         return cudaGetLastError();
     }
+    static uint32_t chk(const uint32_t* w, int use_view) { return check_hash<L>(w, use_view != 0); }
     static const GpuOps* get() {
-        static const GpuOps ops = {L::R, L::V, L::K, L::NW, L::BYTES, (int)(L::BYTES + sizeof(RecHdr)), sizeof(typename ExpandCfg<L>::Smem), ExpandCfg<L>::WARPS * 32,
+        static const GpuOps ops = {chk, L::R, L::V, L::K, L::NW, L::BYTES, (int)(L::BYTES + sizeof(RecHdr)), sizeof(typename ExpandCfg<L>::Smem), ExpandCfg<L>::WARPS * 32,
                                    launch_expand, launch_insert, prepare};
         return &ops;
     }
@@ -400,6 +402,25 @@ int vsr_engine_trace_record(VsrEngine* e, uint64_t local_id, uint64_t* parent_ou
     e->st.bytes_d2h += 8;
     *parent_out = t >> 12;
     *cand_out = (uint32_t)(t & 0xFFF);
+    return 0;
+}
+
+int vsr_engine_lookup(VsrEngine* e, const void* state, int* level_out, int* owner_out) {
+    const ModelOps* ops = e->m->ops;
+    uint64_t fp = ops->fingerprint((const uint32_t*)state, e->m->run.use_view);
+    if (fp == 0) fp = 1;
+    const int owner = e->world > 1 ? (int)(fp >> e->owner_shift) : e->rank;
+    if (owner_out) *owner_out = owner;
+    *level_out = 0;
+    if (owner != e->rank) return 0;
+    const uint32_t chk = e->g->check_hash((const uint32_t*)state, e->m->run.use_view);
+    unsigned long long* d = (unsigned long long*)&e->ctr->work_next; /* scratch word; counters are reset per level */
+    lookup_kernel<<<1, 1, 0, e->stream>>>(e->table, e->table_cap - 1, fp, chk, d);
+    CK(cudaGetLastError());
+    unsigned long long meta = 0;
+    CK(cudaMemcpyAsync(&meta, d, 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    *level_out = (int)(meta >> 56);
     return 0;
 }
 

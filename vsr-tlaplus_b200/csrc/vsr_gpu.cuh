@@ -110,7 +110,7 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) { /* splitmix64 finaliser:
     x ^= x >> 31;
     return x;
 }
-template <class L> __device__ __forceinline__ uint32_t check_hash(const uint32_t* w, bool use_view) {
+template <class L> VSR_HD uint32_t check_hash(const uint32_t* w, bool use_view) {
     /* second, independent 32-bit hash of the VIEW words: lets the seen-set tell fp64 collisions apart */
     constexpr int full = L::VIEW_BITS >> 5, rem = L::VIEW_BITS & 31;
     const int nw = use_view ? (full + (rem ? 1 : 0)) : L::NW;
@@ -175,7 +175,7 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_
 /* ------------------------------------------------------------------ expand kernel */
 
 constexpr int SCAP = 64;      /* staged new states per warp */
-constexpr int QG = 512;       /* queue entries per action group per block round */
+constexpr int QPS = 10;       /* pool entries per parent state (pool = QPS * states per block round) */
 
 template <class L> struct WarpStage {
     alignas(16) uint32_t stage[SCAP * L::NW];    /* new states, packed back to back for the bulk store */
@@ -186,8 +186,9 @@ template <class L, int WARPS> struct BlockSmemT {
     static constexpr int NG = 13;                /* action groups (Ops<L>::NGRP) */
     uint64_t fp_tab[8 * 256];                    /* FP64 slicing-by-8 tables */
     uint32_t par[NS * (L::NW + 1)];              /* parents, row stride NW+1 (odd: bank-conflict-free column reads) */
-    uint16_t queue[NG][QG];                      /* enabled (state, candidate) pairs, one queue per action group */
-    int qcount[NG];
+    static constexpr int QCAP = QPS * NS;
+    uint16_t pool[QCAP];                         /* enabled (state, candidate) pairs, grouped by action (a barrier per group) */
+    int qcount[NG];                              /* pairs found per group (may exceed what the pool holds) */
     int take;
     unsigned long long round_first;
     WarpStage<L> w[WARPS];
@@ -216,7 +217,7 @@ template <class L> struct Expander {
     Smem& B;
     WarpStage<L>& S;
     const int lane, warp, tid;
-    int sn = 0;
+    int sn = 0, gbase = 0;
     unsigned long long gen = 0;
     unsigned probes = 0, coll = 0, ties = 0;
     const uint32_t* mine = nullptr;
@@ -320,7 +321,7 @@ template <class L> struct Expander {
         while (sn >= 32) flush(32);
     }
 
-    /* scan one action group: guards only */
+    /* scan one action group: guards only; enabled pairs go to the block pool */
     template <int G> __device__ __forceinline__ void scan() {
         const int c0 = O_::grp_begin(G), c1 = O_::grp_begin(G + 1);
 #pragma unroll 1
@@ -331,13 +332,13 @@ template <class L> struct Expander {
             if (en) {
                 int base = 0;
                 if (lane == 0) base = atomicAdd(&B.qcount[G], __popc(en));
-                base = __shfl_sync(0xffffffffu, base, 0);
+                base = gbase + __shfl_sync(0xffffffffu, base, 0);
                 if (m > 0) any = true;
-                /* positions below QG are queued; the rest (queue full) are applied right here by their own lanes.
+                /* positions below QCAP are queued; the rest (pool full: rare) are applied right here by their own lanes.
                    The counter only grows, so a position is either queued by exactly one lane or nobody's. */
                 const int pos = base + __popc(en & ((1u << lane) - 1u));
-                const bool inl = m > 0 && pos >= QG;
-                if (m > 0 && !inl) B.queue[G][pos] = (uint16_t)(tid | ((cand - c0) << 9));
+                const bool inl = m > 0 && pos >= Smem::QCAP;
+                if (m > 0 && !inl) B.pool[pos] = (uint16_t)(tid | ((cand - c0) << 9));
                 if (__any_sync(0xffffffffu, inl)) {
                     uint32_t n[L::NW];
                     int mult = 0;
@@ -346,6 +347,10 @@ template <class L> struct Expander {
                 }
             }
         }
+        /* every warp does the same amount of scan work, so this barrier is cheap; after it qcount[G] is final and the
+           next group's pool segment starts where this one ends */
+        __syncthreads();
+        gbase = gbase + B.qcount[G] < Smem::QCAP ? gbase + B.qcount[G] : Smem::QCAP;
     }
     /* apply one batch of <= 32 pairs of group G */
     template <int G> __device__ __noinline__ void apply(int b, int k) {
@@ -353,7 +358,7 @@ template <class L> struct Expander {
         int mult = 0, cand = 0, si = 0;
         const bool act = lane < k;
         if (act) {
-            const unsigned item = B.queue[G][b + lane];
+            const unsigned item = B.pool[b + lane];
             si = item & 511;
             cand = O_::grp_begin(G) + (int)(item >> 9);
             mult = O_::template step_grp<true, G>(P.run, &B.par[si * (L::NW + 1)], cand, n);
@@ -367,6 +372,7 @@ template <class L> struct Expander {
         for (int i = tid; i < count * L::NW; i += NS) B.par[(i / L::NW) * (L::NW + 1) + (i % L::NW)] = __ldg(src + i);
         if (tid < Smem::NG) B.qcount[tid] = 0;
         if (tid == 0) { B.round_first = first; B.take = 0; }
+        gbase = 0;
         __syncthreads();
         have = tid < count;
         mine = &B.par[(have ? tid : 0) * (L::NW + 1)];
@@ -375,11 +381,12 @@ template <class L> struct Expander {
         scan<7>(); scan<8>(); scan<9>(); scan<10>(); scan<11>(); scan<12>();
         if (P.check_deadlock && have && !any) atomicMin(&P.ctr->dead_id, P.in_base + first + tid);
         __syncthreads();
-        /* batches: group g has ceil(min(count_g, QG) / 32) of them */
-        int nb[Smem::NG], total = 0;
+        /* batches: group g has ceil(|group g's pool segment| / 32) of them */
+        int nb[Smem::NG], gs[Smem::NG + 1], total = 0;
+        gs[0] = 0;
         for (int g = 0; g < Smem::NG; g++) {
-            const int c = B.qcount[g] < QG ? B.qcount[g] : QG;
-            nb[g] = (c + 31) >> 5;
+            gs[g + 1] = gs[g] + B.qcount[g] < Smem::QCAP ? gs[g] + B.qcount[g] : Smem::QCAP;
+            nb[g] = (gs[g + 1] - gs[g] + 31) >> 5;
             total += nb[g];
         }
         for (;;) {
@@ -389,8 +396,8 @@ template <class L> struct Expander {
             if (t >= total) break;
             int g = 0;
             while (t >= nb[g]) { t -= nb[g]; g++; }
-            const int c = B.qcount[g] < QG ? B.qcount[g] : QG;
-            const int b = t * 32, k = c - b < 32 ? c - b : 32;
+            const int b = gs[g] + t * 32;
+            const int k = gs[g + 1] - b < 32 ? gs[g + 1] - b : 32;
             switch (g) {
             case 0: apply<0>(b, k); break;   case 1: apply<1>(b, k); break;   case 2: apply<2>(b, k); break;
             case 3: apply<3>(b, k); break;   case 4: apply<4>(b, k); break;   case 5: apply<5>(b, k); break;
@@ -503,6 +510,18 @@ template <class L> __global__ void __launch_bounds__(256) insert_kernel(const In
             } else atomicExch(&P.ctr->overflow, 1);
         }
     }
+}
+
+/* membership query (tests / golden-trace cross-check): meta of the entry holding (fp, check), 0 if absent */
+__global__ void lookup_kernel(const uint64_t* table, unsigned long long mask, uint64_t fp, uint32_t check, unsigned long long* meta_out) {
+    unsigned long long h = mix64(fp) & mask;
+    for (unsigned long long i = 0; i <= mask; i++) {
+        const uint64_t e0 = table[2 * h], e1 = table[2 * h + 1];
+        if (e0 == 0) { *meta_out = 0; return; }
+        if (e0 == fp && (uint32_t)e1 == check) { *meta_out = e1; return; }
+        h = (h + 1) & mask;
+    }
+    *meta_out = 0;
 }
 
 } // namespace vsr

@@ -93,6 +93,13 @@ class GpuEngine:
         self._ck(self.lib.vsr_engine_trace_record(self._e, local_id, C.byref(parent), C.byref(cand)))
         return int(parent.value), int(cand.value)
 
+    def lookup(self, state: bytes) -> Tuple[int, int]:
+        """(depth at which this canonical packed state was first seen on THIS rank's shard or 0, owner rank)"""
+        lvl, owner = C.c_int(), C.c_int()
+        buf = (C.c_uint8 * self.mc.state_bytes).from_buffer_copy(state)
+        self._ck(self.lib.vsr_engine_lookup(self._e, buf, C.byref(lvl), C.byref(owner)))
+        return int(lvl.value), int(owner.value)
+
     def collected(self, level: int) -> bytes:
         n = int(self.lib.vsr_engine_collected(self._e, level, None, 0))
         buf = (C.c_uint8 * max(n * self.mc.state_bytes, 1))()
