@@ -151,6 +151,9 @@ int vsr_engine_set_send_buffers(VsrEngine* e, void* dev_records, uint64_t cap_re
 int vsr_engine_seed_init(VsrEngine* e);                       /* inserts Init if this rank owns it */
 /* expands the current frontier: owned successors go to the seen-set, others to the send buffers */
 int vsr_engine_expand(VsrEngine* e);
+/* same for frontier states [first, first + count) only: lets the host bound the exchange buffers by pumping a wide level
+ * in several sub-wavefronts (send counters restart at 0 for every part) */
+int vsr_engine_expand_part(VsrEngine* e, uint64_t first, uint64_t count);
 /* inserts records received from peers (device pointer) */
 int vsr_engine_insert_records(VsrEngine* e, const void* dev_records, uint64_t n);
 /* finishes the level: resolves ties, swaps frontiers; writes this rank's level numbers */

@@ -66,6 +66,15 @@ class HostEngine:
         if self.owner(fp) == self.rank:
             self._insert(s, fp, self.mc.aux_key(s), ROOT_PARENT, 0, 1)
 
+    def expand_part(self, first, count):
+        full = self.frontier
+        self.frontier = full[first:first + count]
+        self.out = [[] for _ in range(self.world)]
+        try:
+            self.expand()
+        finally:
+            self.frontier = full
+
     def expand(self):
         import ctypes as C
         lib, h, sb = self.mc._lib, self.mc._h, self.sb

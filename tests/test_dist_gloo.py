@@ -25,7 +25,8 @@ def _worker(rank, world, port, cfg, q, kw):
     R, V, L, inv = cfg
     mc = pkg.ModelChecker.from_constants(R, V, L, invariants=inv)
     eng = HostEngine(mc, rank, world)
-    res = vdist.ShardedBfs(eng, rank, world).run(**kw)
+    part = kw.pop("part_states", 0)
+    res = vdist.ShardedBfs(eng, rank, world, part_states=part).run(**kw)
     levels = [sorted(lv) for lv in eng.levels if lv or True]
     trace = vdist.replay_trace(mc, res.trace_cands) if (res.trace_cands or res.rc == 12) and rank == 0 else []
     q.put((rank, dict(rc=res.rc, generated=res.generated, distinct=res.distinct, depth=res.depth, complete=res.complete,
@@ -105,3 +106,14 @@ def test_sharded_violation_and_cross_rank_trace():
     for i in range(len(trace) - 1):
         assert trace[i + 1][1] in [t for t, _, _ in mc.successors(trace[i][1])]
     assert mc.invariant(trace[-1][1]) != 0 and all(mc.invariant(s) == 0 for _, s in trace[:-1])
+
+
+def test_sharded_bfs_in_sub_wavefronts():
+    """wide levels pumped in several expand/exchange/insert sub-steps (bounded exchange buffers) give the same result"""
+    cfg = (2, 2, 2, ("AcknowledgedWriteNotLost",))
+    got = run_world(2, cfg, 29551, part_states=7)
+    o = orc.bfs(orc.params(2, 2, 2), workers=2)
+    for rank, res, levels, _ in got:
+        assert res["rc"] == 0 and res["complete"]
+        assert (res["generated"], res["distinct"], res["depth"]) == (o.generated, o.distinct, o.depth)
+        assert res["level_sizes"] == o.level_sizes

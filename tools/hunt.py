@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--table", type=int, default=0)
     ap.add_argument("--frontier", type=int, default=0)
     ap.add_argument("--send", type=int, default=1 << 20)
+    ap.add_argument("--part", type=int, default=0, help="frontier states per sub-wavefront and rank")
     ap.add_argument("--depth", type=int, default=0)
     ap.add_argument("--seconds", type=float, default=0)
     ap.add_argument("--continue-past", action="store_true")
@@ -50,7 +51,7 @@ def main():
     t0 = time.time()
     eng = vdist.GpuEngine(mc, rank, world, device=local, table_capacity=args.table, frontier_capacity=args.frontier,
                           send_capacity=args.send, keep_trace=True)
-    bfs = vdist.ShardedBfs(eng, rank, world)
+    bfs = vdist.ShardedBfs(eng, rank, world, part_states=args.part)
     t1 = time.time()
     res = bfs.run(max_depth=args.depth, max_seconds=args.seconds, stop_on_violation=not args.continue_past)
     torch.cuda.synchronize(dev)

@@ -126,7 +126,7 @@ EXPORTED_SYMBOLS = [
     "vsr_load", "vsr_load_cfg_text", "vsr_model_create", "vsr_model_free", "vsr_model_info", "vsr_init", "vsr_successors", "vsr_enabled_candidates",
     "vsr_canon", "vsr_fingerprint", "vsr_fingerprint_bytewise", "vsr_aux_key", "vsr_invariant", "vsr_unpack", "vsr_pack", "vsr_state_to_tla",
     "vsr_flat_to_tla", "vsr_action_name", "vsr_action_location", "vsr_bfs", "vsr_engine_create", "vsr_engine_destroy",
-    "vsr_engine_record_bytes", "vsr_engine_set_send_buffers", "vsr_engine_seed_init", "vsr_engine_expand",
+    "vsr_engine_record_bytes", "vsr_engine_set_send_buffers", "vsr_engine_seed_init", "vsr_engine_expand", "vsr_engine_expand_part",
     "vsr_engine_insert_records", "vsr_engine_finish_level", "vsr_engine_frontier_size", "vsr_engine_read_frontier",
     "vsr_engine_trace_record", "vsr_engine_stats", "vsr_engine_reset", "vsr_engine_lookup", "vsr_engine_last_error", "vsr_engine_collected", "vsr_engine_build_trace",
     "vsr_replay_candidates", "vsr_probe_bench", "vsr_version",
@@ -176,6 +176,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.vsr_engine_set_send_buffers.argtypes = [vp, vp, u64, vp]
     lib.vsr_engine_seed_init.argtypes = [vp]
     lib.vsr_engine_expand.argtypes = [vp]
+    lib.vsr_engine_expand_part.argtypes = [vp, u64, u64]
     lib.vsr_engine_insert_records.argtypes = [vp, vp, u64]
     lib.vsr_engine_finish_level.argtypes = [vp, C.POINTER(VsrLevelInfo)]
     lib.vsr_engine_frontier_size.argtypes = [vp]

@@ -282,15 +282,26 @@ int vsr_engine_seed_init(VsrEngine* e) {
     return 0;
 }
 
-int vsr_engine_expand(VsrEngine* e) {
+/* expand frontier states [first, first + count) of the current level (count = 0: nothing to do on this rank) */
+int vsr_engine_expand_part(VsrEngine* e, uint64_t first, uint64_t count) {
     if (!e->level_open) {
         int rc = engine_reset_level(e);
         if (rc) return rc;
     }
-    if (e->n_cur == 0) return 0;
+    if (e->send_count) CK(cudaMemsetAsync(e->send_count, 0, sizeof(unsigned int) * e->world, e->stream));
+    if (first >= e->n_cur) count = 0;
+    if (first + count > e->n_cur) count = e->n_cur - first;
+    if (count == 0) {
+        CK(cudaStreamSynchronize(e->stream));
+        return 0;
+    }
     ExpandParams p;
     fill_params(e, p);
-    const uint64_t want_blocks = (e->n_cur + e->g->states_per_block - 1) / e->g->states_per_block;
+    p.in += first * (uint64_t)e->g->nw;
+    p.n_in = count;
+    p.in_base += first;
+    CK(cudaMemsetAsync(&e->ctr->work_next, 0, sizeof(unsigned long long), e->stream));
+    const uint64_t want_blocks = (count + e->g->states_per_block - 1) / e->g->states_per_block;
     const uint64_t max_blocks = (uint64_t)e->sms * e->blocks_per_sm; /* persistent: whole multiples of the SM count */
     int grid = (int)(want_blocks < max_blocks ? want_blocks : max_blocks);
     if (grid < 1) grid = 1;
@@ -304,6 +315,8 @@ int vsr_engine_expand(VsrEngine* e) {
     e->level_ms_acc += ms;
     return 0;
 }
+
+int vsr_engine_expand(VsrEngine* e) { return vsr_engine_expand_part(e, 0, e->n_cur); }
 
 int vsr_engine_insert_records(VsrEngine* e, const void* dev_records, uint64_t n) {
     if (!e->level_open) {

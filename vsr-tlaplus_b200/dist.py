@@ -60,6 +60,9 @@ class GpuEngine:
     def expand(self):
         self._ck(self.lib.vsr_engine_expand(self._e))
 
+    def expand_part(self, first: int, count: int):
+        self._ck(self.lib.vsr_engine_expand_part(self._e, first, count))
+
     def send_counts(self) -> torch.Tensor:
         torch.cuda.current_stream(self.dev).synchronize()
         return self.send_count.to(torch.int64)
@@ -143,8 +146,9 @@ class ShardedBfs:
 
     ROOT_PARENT = (1 << 52) - 1
 
-    def __init__(self, engine, rank: int, world: int, group=None):
+    def __init__(self, engine, rank: int, world: int, group=None, part_states: int = 0):
         self.e, self.rank, self.world, self.group = engine, rank, world, group
+        self.part_states = part_states  # frontier states per sub-wavefront and rank (0 = whole level at once)
 
     # -- collectives (no-ops when world == 1) ---------------------------------------------------
     def _allreduce(self, vals: List[int], op) -> List[int]:
@@ -171,11 +175,19 @@ class ShardedBfs:
         recv = self.e.new_recv(total)
         rb = self.e.record_bytes
         parts = [self.e.send_slice(p, sc[p]) for p in range(self.world)]
-        inp = torch.cat(parts) if sum(sc) else parts[0][:0]
         out = recv.reshape(-1)[: total * rb]
-        # one variable-size all-to-all (NCCL: grouped send/recv over NVLink; also runs on gloo for the CPU tests)
-        dist.all_to_all_single(out, inp, output_split_sizes=[c * rb for c in rcnt], input_split_sizes=[c * rb for c in sc],
-                               group=self.group)
+        if dist.get_backend(self.group) == "nccl":
+            # grouped send/recv straight out of the per-destination send buffers over NVLink: no staging copy
+            outs, off = [], 0
+            for p in range(self.world):
+                outs.append(out[off * rb:(off + rcnt[p]) * rb])
+                off += rcnt[p]
+            dist.all_to_all(outs, parts, group=self.group)
+        else:
+            # gloo (CPU tests) has no list all-to-all: one variable-size all_to_all_single over a concatenation
+            inp = torch.cat(parts) if sum(sc) else parts[0][:0]
+            dist.all_to_all_single(out, inp, output_split_sizes=[c * rb for c in rcnt], input_split_sizes=[c * rb for c in sc],
+                                   group=self.group)
         self.e.insert(recv, total)
         return sum(sc)
 
@@ -233,8 +245,15 @@ class ShardedBfs:
                 (late,) = self._allreduce([1 if time.time() - t0 >= max_seconds else 0], MAX)
                 if late:
                     break
-            self.e.expand()
-            r.exchanged_records += self._exchange()
+            if self.world == 1 or not self.part_states:
+                self.e.expand()
+                r.exchanged_records += self._exchange()
+            else:
+                # wide level: pump it in sub-wavefronts so the exchange buffers stay bounded
+                (nparts,) = self._allreduce([(self.e.frontier_size() + self.part_states - 1) // self.part_states], MAX)
+                for k in range(max(nparts, 1)):
+                    self.e.expand_part(k * self.part_states, self.part_states)
+                    r.exchanged_records += self._exchange()
         r.rc = result
         r.depth = len(r.level_sizes)
         (r.queue,) = self._allreduce([0 if r.complete else self.e.frontier_size()], SUM)
