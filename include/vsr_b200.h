@@ -186,9 +186,10 @@ int vsr_engine_build_trace(VsrEngine* e, uint64_t local_id, void* trace_out, uin
 int vsr_replay_candidates(const VsrModel* m, const uint32_t* cands, int n, void* trace_out, uint8_t* trace_actions,
                           size_t trace_cap);
 
-/* seen-set micro-benchmark: inserts n splitmix64 keys (dup_frac duplicates) into a
- * table of `capacity` slots; returns device ms per launch in *ms_out. */
-int vsr_probe_bench(int device, uint64_t capacity, uint64_t n, double dup_frac, int iters, double* ms_out);
+/* seen-set micro-benchmark: inserts n splitmix64 keys (a fraction dup_frac of them repeats) into a fresh
+ * table of `capacity` slots (power of two) with the BFS's own insert routine; best of `iters` launches.
+ * out[0] = device ms per launch, out[1] = keys found new (must equal the number of distinct keys), out[2] = slots probed. */
+int vsr_probe_bench(int device, uint64_t capacity, uint64_t n, double dup_frac, int iters, double* out);
 
 const char* vsr_version(void);
 

@@ -158,3 +158,37 @@ def test_published_behaviour_is_inside_the_explored_set(pkg):
         assert eng.lookup(last)[0] == 0
     finally:
         eng.close()
+
+
+def test_view_ties_resolve_to_smallest_aux_key(pkg):
+    """states with equal VIEW but different aux variables arriving in the SAME level.  No configuration explored so
+    far produces one, so inject them through the engine's record interface: three candidates, aux_svc = 2, 0, 1, same VIEW.
+    The level must keep exactly one state — the one with the smallest aux key, whatever the arrival order — with its own
+    trace record, and report the ties."""
+    import struct
+    import torch
+    from vsr_tlaplus_b200 import dist as vdist
+    mc = pkg.ModelChecker.from_constants(3, 2, 2)
+    eng = vdist.GpuEngine(mc, 0, 1, table_capacity=1 << 12, frontier_capacity=1 << 10)
+    try:
+        eng.reset()
+        eng.seed()
+        assert eng.finish().new_states == 1
+        base = [t for t, a, _ in mc.successors(mc.init_state()) if pkg.ACTION_NAMES[a] == "TimerSendSVC"][0]
+        variants = []
+        for aux in (2, 0, 1):
+            f = mc.unpack(base)
+            f.aux_svc = aux
+            variants.append(mc.pack(f))
+        assert len({mc.fingerprint(v) for v in variants}) == 1 and len({mc.aux_key(v) for v in variants}) == 3
+        recs = b"".join(v + struct.pack("<QQQII", mc.fingerprint(v), 0, 0, 100 + i, 1) for i, v in enumerate(variants))
+        t = torch.frombuffer(bytearray(recs), dtype=torch.uint8).cuda()
+        eng.insert(t, 3)
+        li = eng.finish()
+        assert (li.new_states, li.ties, li.generated) == (1, 2, 3)
+        out = (C.c_uint8 * mc.state_bytes)()
+        assert mc._lib.vsr_engine_read_frontier(eng._e, 0, 1, out) == 0
+        assert bytes(out) == variants[1]                       # aux_svc = 0 wins
+        assert eng.trace_record(1) == (0, 101)                 # ... with the trace record of the winner
+    finally:
+        eng.close()

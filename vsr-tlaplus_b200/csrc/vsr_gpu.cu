@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <chrono>
 #include <string>
 #include <vector>
@@ -24,6 +25,8 @@ struct GpuOps {
     int states_per_block;
     cudaError_t (*launch_expand)(const ExpandParams&, int grid, cudaStream_t);
     cudaError_t (*launch_insert)(const InsertParams&, cudaStream_t);
+    cudaError_t (*launch_patch)(const ExpandParams&, const uint8_t* ties, unsigned long long ntie, unsigned long long n_out, cudaStream_t);
+    int tie_bytes;
     cudaError_t (*prepare)(int* blocks_per_sm);
 };
 
@@ -43,10 +46,15 @@ template <class L> struct GpuThunks {
         insert_kernel<L><<<blocks, 256, 0, st>>>(q);
         return cudaGetLastError();
     }
+    static cudaError_t launch_patch(const ExpandParams& p, const uint8_t* ties, unsigned long long ntie, unsigned long long n_out, cudaStream_t st) {
+        if (!n_out) return cudaSuccess;
+        patch_ties_kernel<L><<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(p, ties, ntie, n_out);
+        return cudaGetLastError();
+    }
     static uint32_t chk(const uint32_t* w, int use_view) { return check_hash<L>(w, use_view != 0); }
     static const GpuOps* get() {
         static const GpuOps ops = {chk, L::R, L::V, L::K, L::NW, L::BYTES, (int)(L::BYTES + sizeof(RecHdr)), sizeof(typename ExpandCfg<L>::Smem), ExpandCfg<L>::WARPS * 32,
-                                   launch_expand, launch_insert, prepare};
+                                   launch_expand, launch_insert, launch_patch, (int)(sizeof(TieRec) + L::BYTES), prepare};
         return &ops;
     }
 };
@@ -90,7 +98,7 @@ struct VsrEngine {
     uint64_t* trace = nullptr;
     uint64_t trace_cap = 0;
     DevCounters* ctr = nullptr;
-    TieRec* ties = nullptr;
+    uint8_t* ties = nullptr;
     uint64_t tie_cap = 0;
     uint64_t* fp_tab = nullptr;
     uint8_t* send = nullptr;
@@ -209,7 +217,7 @@ int vsr_engine_create(const VsrModel* m, const VsrRunOpts* opts, int rank, int w
         if ((ce = cudaMalloc(&e->frontier[i], fcap * S)) != cudaSuccess) return bail("cudaMalloc(frontier)", ce);
     if (e->trace_cap && (ce = cudaMalloc(&e->trace, e->trace_cap * 8)) != cudaSuccess) return bail("cudaMalloc(trace)", ce);
     if ((ce = cudaMalloc(&e->ctr, sizeof(DevCounters))) != cudaSuccess) return bail("cudaMalloc", ce);
-    if ((ce = cudaMalloc(&e->ties, e->tie_cap * sizeof(TieRec))) != cudaSuccess) return bail("cudaMalloc", ce);
+    if ((ce = cudaMalloc(&e->ties, e->tie_cap * (size_t)e->g->tie_bytes)) != cudaSuccess) return bail("cudaMalloc", ce);
     if ((ce = cudaMalloc(&e->fp_tab, 8 * 256 * 8)) != cudaSuccess) return bail("cudaMalloc", ce);
     if ((ce = cudaMalloc(&e->init_rec, e->g->rec_bytes)) != cudaSuccess) return bail("cudaMalloc", ce);
     if ((ce = cudaMemcpyAsync(e->fp_tab, fp64_table(), 8 * 256 * 8, cudaMemcpyHostToDevice, e->stream)) != cudaSuccess) return bail("memcpy", ce);
@@ -344,6 +352,44 @@ int vsr_engine_finish_level(VsrEngine* e, VsrLevelInfo* out) {
     CK(cudaMemcpyAsync(&c, e->ctr, sizeof c, cudaMemcpyDeviceToHost, e->stream));
     e->st.bytes_d2h += sizeof c;
     CK(cudaStreamSynchronize(e->stream));
+    if (c.tie_count > 0 && c.tie_count <= e->tie_cap && !c.overflow && c.out_count <= e->frontier_cap) {
+        /* same-level states with equal VIEW but different aux variables.  Keep, per fingerprint, the
+           smallest (aux_key, parent, candidate) among the late arrivals, sorted by fingerprint, and let the patch
+           kernel replace first arrivals that lose; the level's violation verdict is recomputed from scratch. */
+        const size_t tb = (size_t)e->g->tie_bytes;
+        std::vector<uint8_t> host(c.tie_count * tb);
+        CK(cudaMemcpy(host.data(), e->ties, host.size(), cudaMemcpyDeviceToHost));
+        std::vector<const uint8_t*> recs;
+        for (uint64_t i = 0; i < c.tie_count; i++) recs.push_back(host.data() + i * tb);
+        auto key = [](const uint8_t* r) { return (const TieRec*)r; };
+        std::sort(recs.begin(), recs.end(), [&](const uint8_t* a, const uint8_t* b) {
+            const TieRec *x = key(a), *y = key(b);
+            if (x->fp != y->fp) return x->fp < y->fp;
+            if (x->check != y->check) return x->check < y->check;
+            if (x->auxkey != y->auxkey) return x->auxkey < y->auxkey;
+            if (x->parent != y->parent) return x->parent < y->parent;
+            return x->cand < y->cand;
+        });
+        std::vector<uint8_t> best;
+        uint64_t nbest = 0;
+        for (size_t i = 0; i < recs.size(); i++) {
+            if (i && key(recs[i])->fp == key(recs[i - 1])->fp && key(recs[i])->check == key(recs[i - 1])->check) continue;
+            best.insert(best.end(), recs[i], recs[i] + tb);
+            nbest++;
+        }
+        CK(cudaMemcpy(e->ties, best.data(), best.size(), cudaMemcpyHostToDevice));
+        static const unsigned long long ones = ~0ull;
+        CK(cudaMemcpy(&e->ctr->viol_id, &ones, 8, cudaMemcpyHostToDevice));
+        CK(cudaMemset(&e->ctr->viol_which, 0, sizeof(int)));
+        ExpandParams p;
+        fill_params(e, p);
+        CK(e->g->launch_patch(p, e->ties, nbest, c.out_count, e->stream));
+        e->st.kernel_launches++;
+        CK(cudaMemcpyAsync(&c, e->ctr, sizeof c, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        e->st.bytes_d2h += host.size() + sizeof c;
+        e->st.bytes_h2d += best.size();
+    }
     VsrLevelInfo li;
     memset(&li, 0, sizeof li);
     li.new_states = c.out_count;
@@ -535,6 +581,41 @@ int vsr_bfs(const VsrModel* m, const VsrRunOpts* opts, VsrStats* stats, void* tr
     return result;
 }
 
-int vsr_probe_bench(int, uint64_t, uint64_t, double, int, double*) { return VSR_RC_ERROR; }
+int vsr_probe_bench(int device, uint64_t capacity, uint64_t n, double dup_frac, int iters, double* ms_out) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return VSR_RC_SYSTEM;
+    if (capacity & (capacity - 1)) return VSR_RC_ERROR;
+    cudaSetDevice(device);
+    uint64_t* table = nullptr;
+    unsigned long long* cnt = nullptr;
+    if (cudaMalloc(&table, capacity * 16) != cudaSuccess) return VSR_RC_SYSTEM;
+    if (cudaMalloc(&cnt, 16) != cudaSuccess) { cudaFree(table); return VSR_RC_SYSTEM; }
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    const unsigned long long distinct = (unsigned long long)((double)n * (1.0 - dup_frac)) + 1;
+    double best = 1e30;
+    unsigned long long h[2] = {0, 0};
+    for (int it = 0; it < iters + 1; it++) { /* first pass is warm-up */
+        cudaMemset(table, 0, capacity * 16);
+        cudaMemset(cnt, 0, 16);
+        cudaEventRecord(a);
+        probe_bench_kernel<<<prop.multiProcessorCount * 8, 256>>>(table, capacity - 1, n, distinct, 1 + it, cnt, cnt + 1);
+        cudaEventRecord(b);
+        if (cudaEventSynchronize(b) != cudaSuccess) { cudaFree(table); cudaFree(cnt); return VSR_RC_SYSTEM; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        if (it > 0 && ms < best) best = ms;
+        cudaMemcpy(h, cnt, 16, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(table);
+    cudaFree(cnt);
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    if (ms_out) { ms_out[0] = best; ms_out[1] = (double)h[0]; ms_out[2] = (double)h[1]; }
+    return h[0] == (distinct < n ? distinct : n) ? 0 : VSR_RC_ERROR;
+}
 
 } /* extern "C" */

@@ -46,6 +46,7 @@ struct DevCounters {
     int _pad;
 };
 
+/* a same-level VIEW tie: header, then the candidate's L::NW packed words */
 struct TieRec {
     uint64_t fp;
     uint64_t parent;
@@ -72,7 +73,7 @@ struct ExpandParams {
     uint64_t* trace;             /* per local id: make_trec(parent global id, candidate); may be null */
     unsigned long long trace_cap;
     DevCounters* ctr;
-    TieRec* ties;
+    uint8_t* ties;               /* tie_cap entries of sizeof(TieRec) + L::BYTES */
     unsigned long long tie_cap;
     const uint64_t* fp_tab;      /* 8 x 256 FP64 slicing tables */
     RunCfg run;
@@ -290,7 +291,9 @@ template <class L> struct Expander {
                         if (t < P.tie_cap) {
                             TieRec rec;
                             rec.fp = fp; rec.parent = parent_gid; rec.auxkey = auxkey; rec.cand = (uint32_t)cand; rec.check = chk; rec._pad = 0;
-                            P.ties[t] = rec;
+                            uint8_t* dst = P.ties + t * (sizeof(TieRec) + L::BYTES);
+                            *(TieRec*)dst = rec;
+                            for (int j = 0; j < L::NW; j++) ((uint32_t*)(dst + sizeof(TieRec)))[j] = n[j];
                         } else atomicExch(&P.ctr->overflow, 2);
                     }
                 } else {
@@ -473,7 +476,9 @@ template <class L> __global__ void __launch_bounds__(256) insert_kernel(const In
                 TieRec tr;
                 tr.fp = h->fp; tr.parent = h->parent; tr.auxkey = (uint32_t)((meta >> 32) & 0xFFFFFF); tr.cand = h->cand;
                 tr.check = (uint32_t)meta; tr._pad = 0;
-                P.ties[t] = tr;
+                uint8_t* dst = P.ties + t * (sizeof(TieRec) + L::BYTES);
+                *(TieRec*)dst = tr;
+                for (int j = 0; j < L::NW; j++) ((uint32_t*)(dst + sizeof(TieRec)))[j] = n[j];
             } else atomicExch(&P.ctr->overflow, 2);
         }
     }
@@ -512,6 +517,43 @@ template <class L> __global__ void __launch_bounds__(256) insert_kernel(const In
     }
 }
 
+/* VIEW-tie patch pass (only launched for a level that reported ties).  `ties` holds, sorted by fp, ONE
+   record per tied fingerprint: the smallest (aux_key, parent, candidate) among the late arrivals.  Every state of the
+   new level looks itself up; if a tie record beats the first arrival's aux_key, the state and its trace record are
+   replaced, so the survivor is "smallest aux_key wins" whatever the arrival order — the rule the oracle applies.
+   The invariant is re-evaluated on every state of the level (the verdict may change with the aux variables). */
+template <class L> __global__ void patch_ties_kernel(const ExpandParams P, const uint8_t* ties, unsigned long long ntie, unsigned long long n_out) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    uint32_t w[L::NW];
+    uint32_t* st = P.out + i * L::NW;
+    for (int j = 0; j < L::NW; j++) w[j] = st[j];
+    uint64_t fp = fp64_view8<L>(P.fp_tab, w, P.run.use_view != 0);
+    if (fp == 0) fp = 1;
+    const uint32_t chk = check_hash<L>(w, P.run.use_view != 0);
+    const size_t stride = sizeof(TieRec) + L::BYTES;
+    unsigned long long lo = 0, hi = ntie;
+    while (lo < hi) {
+        const unsigned long long mid = (lo + hi) / 2;
+        if (((const TieRec*)(ties + mid * stride))->fp < fp) lo = mid + 1; else hi = mid;
+    }
+    for (; lo < ntie; lo++) {
+        const TieRec* t = (const TieRec*)(ties + lo * stride);
+        if (t->fp != fp) break;
+        if (t->check != chk) continue;
+        if (t->auxkey < Ops<L>::aux_key(w)) {
+            const uint32_t* tw = (const uint32_t*)((const uint8_t*)t + sizeof(TieRec));
+            for (int j = 0; j < L::NW; j++) { w[j] = tw[j]; st[j] = tw[j]; }
+            if (P.trace && P.out_base + i < P.trace_cap) P.trace[P.out_base + i] = make_trec(t->parent, t->cand);
+        }
+    }
+    const int bad = Ops<L>::invariant(P.run, w);
+    if (bad) {
+        atomicMin(&P.ctr->viol_id, P.out_base + i);
+        atomicOr(&P.ctr->viol_which, bad);
+    }
+}
+
 /* membership query (tests / golden-trace cross-check): meta of the entry holding (fp, check), 0 if absent */
 __global__ void lookup_kernel(const uint64_t* table, unsigned long long mask, uint64_t fp, uint32_t check, unsigned long long* meta_out) {
     unsigned long long h = mix64(fp) & mask;
@@ -522,6 +564,30 @@ __global__ void lookup_kernel(const uint64_t* table, unsigned long long mask, ui
         h = (h + 1) & mask;
     }
     *meta_out = 0;
+}
+
+/* seen-set micro-benchmark: n splitmix64 keys, a fraction of them duplicates, inserted with the same
+   table_insert the BFS uses; nothing else in the loop, so its rate is the random-probe ceiling of this table design */
+__global__ void probe_bench_kernel(uint64_t* table, unsigned long long mask, unsigned long long n, unsigned long long distinct,
+                                   unsigned long long seed, unsigned long long* new_count, unsigned long long* probe_count) {
+    unsigned long long mine_new = 0;
+    unsigned probes = 0, coll = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        unsigned long long z = seed + (i % distinct) * 0x9E3779B97F4A7C15ULL; /* splitmix64 of the key index */
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        z ^= z >> 31;
+        if (z == 0) z = 1;
+        mine_new += table_insert(table, mask, z, make_meta(1, 0, (uint32_t)(z >> 32) | 1u), probes, coll) == INS_NEW;
+    }
+    for (int o = 16; o; o >>= 1) {
+        mine_new += __shfl_xor_sync(0xffffffffu, mine_new, o);
+        probes += __shfl_xor_sync(0xffffffffu, probes, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(new_count, mine_new);
+        atomicAdd(probe_count, (unsigned long long)probes);
+    }
 }
 
 } // namespace vsr
