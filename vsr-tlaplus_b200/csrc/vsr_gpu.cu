@@ -104,6 +104,8 @@ struct VsrEngine {
     uint8_t* send = nullptr;
     uint64_t send_cap = 0;
     unsigned int* send_count = nullptr;
+    uint64_t* sent_cache = nullptr;
+    uint64_t sent_cap = 0;
     uint8_t* init_rec = nullptr;
     /* BFS position */
     int cur = 0;                 /* which frontier buffer is the current level */
@@ -154,6 +156,8 @@ static void fill_params(VsrEngine* e, ExpandParams& p) {
     p.send = e->send;
     p.send_cap = e->send_cap;
     p.send_count = e->send_count;
+    p.sent_cache = e->sent_cache;
+    p.sent_mask = e->sent_cap ? e->sent_cap - 1 : 0;
 }
 
 extern "C" {
@@ -219,6 +223,11 @@ int vsr_engine_create(const VsrModel* m, const VsrRunOpts* opts, int rank, int w
     if ((ce = cudaMalloc(&e->ctr, sizeof(DevCounters))) != cudaSuccess) return bail("cudaMalloc", ce);
     if ((ce = cudaMalloc(&e->ties, e->tie_cap * (size_t)e->g->tie_bytes)) != cudaSuccess) return bail("cudaMalloc", ce);
     if ((ce = cudaMalloc(&e->fp_tab, 8 * 256 * 8)) != cudaSuccess) return bail("cudaMalloc", ce);
+    if (world > 1) { /* sender-side duplicate filter: 1/8 of the seen-set's slots, 8 B each */
+        e->sent_cap = tcap / 8 < (1ull << 16) ? (1ull << 16) : tcap / 8;
+        if ((ce = cudaMalloc(&e->sent_cache, e->sent_cap * 8)) != cudaSuccess) return bail("cudaMalloc(sent filter)", ce);
+        if ((ce = cudaMemsetAsync(e->sent_cache, 0, e->sent_cap * 8, e->stream)) != cudaSuccess) return bail("memset", ce);
+    }
     if ((ce = cudaMalloc(&e->init_rec, e->g->rec_bytes)) != cudaSuccess) return bail("cudaMalloc", ce);
     if ((ce = cudaMemcpyAsync(e->fp_tab, fp64_table(), 8 * 256 * 8, cudaMemcpyHostToDevice, e->stream)) != cudaSuccess) return bail("memcpy", ce);
     e->st.table_capacity = tcap;
@@ -241,6 +250,7 @@ void vsr_engine_destroy(VsrEngine* e) {
     cudaFree(e->ties);
     cudaFree(e->fp_tab);
     cudaFree(e->init_rec);
+    cudaFree(e->sent_cache);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -485,6 +495,7 @@ int vsr_engine_lookup(VsrEngine* e, const void* state, int* level_out, int* owne
 
 int vsr_engine_reset(VsrEngine* e) {
     CK(cudaMemsetAsync(e->table, 0, e->table_cap * 16, e->stream));
+    if (e->sent_cache) CK(cudaMemsetAsync(e->sent_cache, 0, e->sent_cap * 8, e->stream));
     const uint64_t tc = e->st.table_capacity, fc = e->st.frontier_capacity, bt = e->st.bytes_table, bf = e->st.bytes_frontier;
     memset(&e->st, 0, sizeof e->st);
     e->st.table_capacity = tc; e->st.frontier_capacity = fc; e->st.bytes_table = bt; e->st.bytes_frontier = bf;

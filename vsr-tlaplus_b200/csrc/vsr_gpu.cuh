@@ -83,6 +83,8 @@ struct ExpandParams {
     uint8_t* send;               /* world * send_cap records of (L::BYTES + sizeof(RecHdr)) */
     unsigned long long send_cap;
     unsigned int* send_count;    /* world counters */
+    uint64_t* sent_cache;        /* direct-mapped filter of (fingerprint, aux key) pairs already shipped to their owner */
+    unsigned long long sent_mask;
 };
 
 struct InsertParams {
@@ -112,15 +114,16 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) { /* splitmix64 finaliser:
     return x;
 }
 template <class L> VSR_HD uint32_t check_hash(const uint32_t* w, bool use_view) {
-    /* second, independent 32-bit hash of the VIEW words: lets the seen-set tell fp64 collisions apart */
+    /* second, independent 32-bit hash of the VIEW words (3 instructions per word + finaliser): lets the seen-set tell
+       fp64 collisions apart instead of silently merging two states as a bare fingerprint set would */
     constexpr int full = L::VIEW_BITS >> 5, rem = L::VIEW_BITS & 31;
     const int nw = use_view ? (full + (rem ? 1 : 0)) : L::NW;
     uint32_t h = 0x9747b28cu;
     for (int i = 0; i < nw; i++) {
         uint32_t k = w[i];
         if (use_view && i == full) k &= (1u << rem) - 1u;
-        k *= 0xcc9e2d51u; k = (k << 15) | (k >> 17); k *= 0x1b873593u;
-        h ^= k; h = (h << 13) | (h >> 19); h = h * 5u + 0xe6546b64u;
+        h ^= k;
+        h = ((h << 13) | (h >> 19)) * 5u + 0xe6546b64u;
     }
     h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
     return h;
@@ -137,30 +140,37 @@ __device__ __forceinline__ uint64_t make_meta(int level, uint32_t auxkey, uint32
     return ((uint64_t)(uint32_t)level << 56) | ((uint64_t)(auxkey & 0xFFFFFFu) << 32) | check;
 }
 
-/* lock-free insert-if-absent; linear probing over 16-byte entries */
-__device__ __forceinline__ int table_insert(uint64_t* table, unsigned long long mask, uint64_t fp, uint64_t meta,
-                                            unsigned& probes, unsigned& collisions) {
-    unsigned long long h = mix64(fp) & mask;
+/* lock-free insert-if-absent; linear probing over 16-byte entries.  (e0, e1) is the entry at the home slot, loaded by the
+   caller as early as the fingerprint was known so that the HBM round trip overlaps the rest of the successor's work. */
+__device__ __forceinline__ unsigned long long table_home(unsigned long long mask, uint64_t fp) { return mix64(fp) & mask; }
+__device__ __forceinline__ int table_insert_from(uint64_t* table, unsigned long long mask, unsigned long long h, uint64_t e0, uint64_t e1,
+                                                 uint64_t fp, uint64_t meta, unsigned& probes, unsigned& collisions) {
     for (;;) {
-        uint64_t e0, e1;
-        ld128_cg(table + 2 * h, e0, e1);
         probes++;
         if (e0 == 0) {
             cas128(table + 2 * h, fp, meta, e0, e1);
             if (e0 == 0 && e1 == 0) return INS_NEW;
-        } else if (e1 == 0) {
-            continue; /* torn read of an entry being published: look again */
         }
-        if (e0 == fp) {
-            if ((uint32_t)e1 == (uint32_t)meta) {
-                const bool same_level = (e1 >> 56) == (meta >> 56);
-                const bool same_aux = ((e1 >> 32) & 0xFFFFFF) == ((meta >> 32) & 0xFFFFFF);
-                return (same_level && !same_aux) ? INS_TIE : INS_DUP;
+        if (e1 != 0) { /* e1 == 0 with e0 != 0: torn read of an entry being published: look again */
+            if (e0 == fp) {
+                if ((uint32_t)e1 == (uint32_t)meta) {
+                    const bool same_level = (e1 >> 56) == (meta >> 56);
+                    const bool same_aux = ((e1 >> 32) & 0xFFFFFF) == ((meta >> 32) & 0xFFFFFF);
+                    return (same_level && !same_aux) ? INS_TIE : INS_DUP;
+                }
+                collisions++;
             }
-            collisions++;
+            h = (h + 1) & mask;
         }
-        h = (h + 1) & mask;
+        ld128_cg(table + 2 * h, e0, e1);
     }
+}
+__device__ __forceinline__ int table_insert(uint64_t* table, unsigned long long mask, uint64_t fp, uint64_t meta,
+                                            unsigned& probes, unsigned& collisions) {
+    const unsigned long long h = table_home(mask, fp);
+    uint64_t e0, e1;
+    ld128_cg(table + 2 * h, e0, e1);
+    return table_insert_from(table, mask, h, e0, e1, fp, meta, probes, collisions);
 }
 
 /* TMA bulk store shared -> global of `bytes` (multiple of 16), issued by one lane; waits until the
@@ -274,15 +284,19 @@ template <class L> struct Expander {
             } else if (mult > 0) {
                 uint64_t fp = fp64_view8<L>(B.fp_tab, n, P.run.use_view != 0);
                 if (fp == 0) fp = 1;
+                const int owner = P.world > 1 ? (int)(fp >> P.owner_shift) : P.rank;
+                /* start the seen-set probe now; the check hash, aux key and tags are computed under its latency */
+                const unsigned long long home = table_home(P.table_mask, fp);
+                ulonglong2 first = make_ulonglong2(0, 0);
+                if (owner == P.rank) first = __ldcg(reinterpret_cast<const ulonglong2*>(P.table + 2 * home));
                 const uint32_t chk = check_hash<L>(n, P.run.use_view != 0);
                 const uint32_t auxkey = O_::aux_key(n);
                 const uint64_t meta = make_meta(P.level, auxkey, chk);
                 const uint64_t parent_gid = make_gid(P.rank, P.in_base + B.round_first + si);
                 trec = make_trec(parent_gid, (uint32_t)cand);
-                const int owner = P.world > 1 ? (int)(fp >> P.owner_shift) : P.rank;
                 if (owner == P.rank) {
                     gen += (unsigned long long)mult; /* successors sent to a peer are counted where they are inserted */
-                    const int r = table_insert(P.table, P.table_mask, fp, meta, probes, coll);
+                    const int r = table_insert_from(P.table, P.table_mask, home, first.x, first.y, fp, meta, probes, coll);
                     isnew = r == INS_NEW;
                     if (isnew) bad = O_::invariant(P.run, n);
                     if (r == INS_TIE) {
@@ -296,7 +310,12 @@ template <class L> struct Expander {
                             for (int j = 0; j < L::NW; j++) ((uint32_t*)(dst + sizeof(TieRec)))[j] = n[j];
                         } else atomicExch(&P.ctr->overflow, 2);
                     }
+                } else if (P.sent_cache && P.sent_cache[mix64(fp ^ auxkey) & P.sent_mask] == (fp ^ ((uint64_t)auxkey << 40))) {
+                    /* this exact (VIEW, aux) pair was already shipped to its owner earlier in the run: a duplicate for
+                       sure, so it is counted here and not sent again (most generated successors are duplicates) */
+                    gen += (unsigned long long)mult;
                 } else {
+                    if (P.sent_cache) P.sent_cache[mix64(fp ^ auxkey) & P.sent_mask] = fp ^ ((uint64_t)auxkey << 40);
                     const unsigned idx = atomicAdd(&P.send_count[owner], 1u);
                     if (idx < P.send_cap) {
                         uint8_t* rec = P.send + ((size_t)owner * P.send_cap + idx) * (L::BYTES + sizeof(RecHdr));
@@ -437,12 +456,14 @@ template <class L> __global__ void __launch_bounds__(ExpandCfg<L>::WARPS * 32, 2
     __shared__ unsigned long long next_round;
     Expander<L> X(P, B);
     const unsigned long long nrounds = (P.n_in + Smem::NS - 1) / Smem::NS;
+    if (threadIdx.x == 0) next_round = atomicAdd(&P.ctr->work_next, 1ull);
     for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) next_round = atomicAdd(&P.ctr->work_next, 1ull);
-        __syncthreads();
         const unsigned long long c = next_round;
+        __syncthreads();
         if (c >= nrounds) break;
+        /* claim the round after this one now: the global atomic's latency hides under this round's work */
+        if (threadIdx.x == 0) next_round = atomicAdd(&P.ctr->work_next, 1ull);
         const unsigned long long first = c * Smem::NS;
         const int count = (int)((P.n_in - first) < (unsigned long long)Smem::NS ? (P.n_in - first) : Smem::NS);
         X.run_round(first, count);
