@@ -177,12 +177,18 @@ class ShardedBfs:
         parts = [self.e.send_slice(p, sc[p]) for p in range(self.world)]
         out = recv.reshape(-1)[: total * rb]
         if dist.get_backend(self.group) == "nccl":
-            # grouped send/recv straight out of the per-destination send buffers over NVLink: no staging copy
-            outs, off = [], 0
+            # grouped ncclSend/ncclRecv straight out of the per-destination send buffers over NVLink: no staging copy;
+            # pairs with nothing to move are skipped on both sides (both know the counts)
+            ops, off = [], 0
             for p in range(self.world):
-                outs.append(out[off * rb:(off + rcnt[p]) * rb])
+                if rcnt[p]:
+                    ops.append(dist.P2POp(dist.irecv, out[off * rb:(off + rcnt[p]) * rb], p, self.group))
                 off += rcnt[p]
-            dist.all_to_all(outs, parts, group=self.group)
+                if sc[p]:
+                    ops.append(dist.P2POp(dist.isend, parts[p], p, self.group))
+            if ops:
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
         else:
             # gloo (CPU tests) has no list all-to-all: one variable-size all_to_all_single over a concatenation
             inp = torch.cat(parts) if sum(sc) else parts[0][:0]
