@@ -217,10 +217,26 @@ def main():
     achieved = (res.distinct / world) * args.steps * b_alg / kern_s / 1e9
     peak, peak_src = peaks()
 
+    # the seen-set's own ceiling (SURVEY §8d "probe_peak"): the BFS's insert routine alone on random keys, same table size
+    probe = None
+    if rank == 0:
+        eng_probe_out = (C.c_double * 3)()
+        torch.cuda.synchronize(dev)
     # e2e: the public one-call API with host buffers in and out (N=1: vsr_bfs; N>1: the same pump incl. engine creation)
     eng.close()
     del eng
     torch.cuda.empty_cache()
+    barrier()
+    if rank == 0:
+        nkeys = 1 << 27
+        rc = pkg.load_library().vsr_probe_bench(local, table_cap, nkeys, 0.5, 3, eng_probe_out)
+        if rc == 0:
+            peak_probes = eng_probe_out[2] / (eng_probe_out[0] / 1e3)
+            ach_probes = int(st.probe_total) / (kern_s / args.steps)   # this rank's probes in the last timed step
+            probe = {"unit": "probes/s", "peak": peak_probes, "achieved": ach_probes, "frac": ach_probes / peak_probes,
+                     "how": "vsr_probe_bench: %d splitmix64 keys (50%% repeats) into a fresh table of %d slots with the BFS's own "
+                            "insert routine, best of 3: %.3f ms; achieved = this rank's seen-set probes per kernel-second of the BFS"
+                            % (nkeys, table_cap, eng_probe_out[0])}
     barrier()
     te = time.time()
     if world == 1:
@@ -263,6 +279,7 @@ def main():
                          "kernel": "expand_kernel<Layout<3,2,3>> (per-GPU states x B_alg / sum of per-level kernel time, max over ranks)"},
             "e2e": {"value": e2e_states / e2e_s, "unit": "states/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "seconds": e2e_s, "api": "ModelChecker.from_cfg_text(cfg).check()" if world == 1 else "dist.GpuEngine + dist.ShardedBfs.run()"},
+            "probe_roofline": probe,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
