@@ -35,7 +35,7 @@ template <class L> struct Ops {
     static VSR_HD int oidx(int a, int b) { return b < a ? b : b - 1; }   /* index of b among replicas \ {a} */
     static VSR_HD int oinv(int a, int i) { return i < a ? i : i + 1; }
 
-    template <int B> static VSR_HD int loglen(const uint32_t* w, int row) {
+    template <int B, class W> static VSR_HD int loglen(const W& w, int row) {
         int n = 0;
         for (int i = 0; i < V; i++) {
             if (fget<B, L::OB>(w, row * V + i) == 0) break;
@@ -43,24 +43,24 @@ template <class L> struct Ops {
         }
         return n;
     }
-    template <int BD, int BS> static VSR_HD void logcopy(uint32_t* wd, int rowd, const uint32_t* ws, int rows) {
+    template <int BD, int BS, class WD, class WS> static VSR_HD void logcopy(const WD& wd, int rowd, const WS& ws, int rows) {
         for (int i = 0; i < V; i++) fset<BD, L::OB>(wd, rowd * V + i, fget<BS, L::OB>(ws, rows * V + i));
     }
-    template <int B> static VSR_HD void logclear(uint32_t* w, int row) {
+    template <int B, class W> static VSR_HD void logclear(const W& w, int row) {
         for (int i = 0; i < V; i++) fset<B, L::OB>(w, row * V + i, 0);
     }
-    static VSR_HD int popmask_svc(const uint32_t* w, int r) {
+    template <class W> static VSR_HD int popmask_svc(const W& w, int r) {
         int n = 0;
         for (int s = 0; s < R; s++) n += (int)VGET(L, SVC_MASK, w, r * R + s);
         return n;
     }
-    static VSR_HD int popmask_dvc(const uint32_t* w, int r) {
+    template <class W> static VSR_HD int popmask_dvc(const W& w, int r) {
         int n = 0;
         for (int s = 0; s < R; s++) n += (int)VGET(L, DVC_MASK, w, r * R + s);
         return n;
     }
     /* ResetRecvMsgs, VSR.tla:299-301 (the self-DVC payload lives and dies with rep_dvc_recv[r]) */
-    static VSR_HD void reset_recv(uint32_t* w, int r) {
+    template <class W> static VSR_HD void reset_recv(const W& w, int r) {
         for (int s = 0; s < R; s++) {
             VSET(L, SVC_MASK, w, r * R + s, 0);
             VSET(L, DVC_MASK, w, r * R + s, 0);
@@ -69,19 +69,19 @@ template <class L> struct Ops {
         VSET(L, SELF_LNV, w, r, 0);
         VSET(L, SELF_COMMIT, w, r, 0);
     }
-    static VSR_HD void reset_dvc_only(uint32_t* w, int r) {
+    template <class W> static VSR_HD void reset_dvc_only(const W& w, int r) {
         for (int s = 0; s < R; s++) VSET(L, DVC_MASK, w, r * R + s, 0);
         logclear<L::SELF_LOG_B>(w, r);
         VSET(L, SELF_LNV, w, r, 0);
         VSET(L, SELF_COMMIT, w, r, 0);
     }
-    static VSR_HD void reset_sent(uint32_t* w, int r) { /* ResetSentVars :303-305 */
+    template <class W> static VSR_HD void reset_sent(const W& w, int r) { /* ResetSentVars :303-305 */
         VSET(L, SENT_DVC, w, r, 0);
         VSET(L, SENT_SV, w, r, 0);
     }
     static VSR_HD int svc_slot(int v, int s, int d) { return ((v - 2) * R + s) * O + oidx(s, d); }
     /* Broadcast(NewSVCMessage(r, v), r): BroadcastFunc :233-240 */
-    static VSR_HD int broadcast_svc(uint32_t* w, int v, int s) {
+    template <class W> static VSR_HD int broadcast_svc(const W& w, int v, int s) {
         for (int dp = 0; dp < O; dp++) {
             const int idx = ((v - 2) * R + s) * O + dp;
             if (VGET(L, SVC_ST, w, idx) != ST_ABSENT) return E_SLOT_OCCUPIED;
@@ -89,7 +89,7 @@ template <class L> struct Ops {
         }
         return 0;
     }
-    static VSR_HD int ncreated(const uint32_t* w) {
+    template <class W> static VSR_HD int ncreated(const W& w) {
         int c = 0;
         for (int x = 0; x < V; x++) c += VGET(L, PR_VIEW, w, x) != 0;
         return c;
@@ -103,20 +103,20 @@ template <class L> struct Ops {
                                  L::C_RPOK, L::C_EXEC, L::C_SGS, L::C_RGS, L::C_RNS, L::NCAND};
         return b[g];
     }
-    template <bool APPLY> static VSR_HD int step(const RunCfg& run, const uint32_t* s, int cand, uint32_t* n) {
-        return cand < L::C_HSVC ? step_grp<APPLY, 0>(run, s, cand, n) : cand < L::C_SDVC ? step_grp<APPLY, 1>(run, s, cand, n)
-             : cand < L::C_HDVC ? step_grp<APPLY, 2>(run, s, cand, n) : cand < L::C_SSV ? step_grp<APPLY, 3>(run, s, cand, n)
-             : cand < L::C_RSV ? step_grp<APPLY, 4>(run, s, cand, n) : cand < L::C_CREQ ? step_grp<APPLY, 5>(run, s, cand, n)
-             : cand < L::C_RPREP ? step_grp<APPLY, 6>(run, s, cand, n) : cand < L::C_RPOK ? step_grp<APPLY, 7>(run, s, cand, n)
-             : cand < L::C_EXEC ? step_grp<APPLY, 8>(run, s, cand, n) : cand < L::C_SGS ? step_grp<APPLY, 9>(run, s, cand, n)
-             : cand < L::C_RGS ? step_grp<APPLY, 10>(run, s, cand, n) : cand < L::C_RNS ? step_grp<APPLY, 11>(run, s, cand, n)
-             : step_grp<APPLY, 12>(run, s, cand, n);
+    template <bool APPLY, class S, class N> static VSR_HD int step(const RunCfg& run, const S& s, int cand, const N& n) {
+        return cand < L::C_HSVC ? step_grp<APPLY, 0, S, N>(run, s, cand, n) : cand < L::C_SDVC ? step_grp<APPLY, 1, S, N>(run, s, cand, n)
+             : cand < L::C_HDVC ? step_grp<APPLY, 2, S, N>(run, s, cand, n) : cand < L::C_SSV ? step_grp<APPLY, 3, S, N>(run, s, cand, n)
+             : cand < L::C_RSV ? step_grp<APPLY, 4, S, N>(run, s, cand, n) : cand < L::C_CREQ ? step_grp<APPLY, 5, S, N>(run, s, cand, n)
+             : cand < L::C_RPREP ? step_grp<APPLY, 6, S, N>(run, s, cand, n) : cand < L::C_RPOK ? step_grp<APPLY, 7, S, N>(run, s, cand, n)
+             : cand < L::C_EXEC ? step_grp<APPLY, 8, S, N>(run, s, cand, n) : cand < L::C_SGS ? step_grp<APPLY, 9, S, N>(run, s, cand, n)
+             : cand < L::C_RGS ? step_grp<APPLY, 10, S, N>(run, s, cand, n) : cand < L::C_RNS ? step_grp<APPLY, 11, S, N>(run, s, cand, n)
+             : step_grp<APPLY, 12, S, N>(run, s, cand, n);
     }
     /* one group's guard (+ effect when APPLY): only this group's code is instantiated, so the device can scan a
        group's candidates in a tight loop */
-    template <bool APPLY, int GRP> static VSR_HD int step_grp(const RunCfg& run, const uint32_t* s, int cand, uint32_t* n) {
-        if (APPLY) {
-            for (int i = 0; i < L::NW; i++) n[i] = s[i];
+    template <bool APPLY, int GRP, class S, class N> static VSR_HD int step_grp(const RunCfg& run, const S& s, int cand, const N& n) {
+        if constexpr (APPLY) {
+            for (int i = 0; i < L::NW; i++) wrw(n, i, rdw(s, i));
         }
         /* ---- TimerSendSVC, VSR.tla:578-590 */
         if constexpr (GRP == 0) {
@@ -495,7 +495,7 @@ template <class L> struct Ops {
     }
 
     /* invariants, VSR.tla:926-952; returns 0 if all selected hold, else the mask bit of the violated one */
-    static VSR_HD int invariant(const RunCfg& run, const uint32_t* w) {
+    template <class W> static VSR_HD int invariant(const RunCfg& run, const W& w) {
         if (!(run.invariant & 3)) return 0; /* NoLogDivergence is vacuous (r1/r1, :931), TestInv is TRUE */
         for (int x = 0; x < V; x++) {
             if (VGET(L, ACKED, w, x) != ACK_TRUE) continue;
@@ -513,7 +513,7 @@ template <class L> struct Ops {
 
     /* label-independent key of the aux variables for same-level VIEW ties; same
        number the oracle's aux_key() computes */
-    static VSR_HD uint32_t aux_key(const uint32_t* w) {
+    template <class W> static VSR_HD uint32_t aux_key(const W& w) {
         uint32_t k = VGET(L, AUX_SVC, w, 0);
         k = k * 16u; /* aux_restart = 0 */
         for (int x = 0; x < V; x++) k = k * 3u + VGET(L, ACKED, w, x);
@@ -654,7 +654,7 @@ inline void fp64_build_slices(uint64_t s8[8 * 256]) {
         }
 }
 
-template <class L> VSR_HD uint64_t fp64_view8(const uint64_t* __restrict__ s8, const uint32_t* w, bool use_view) {
+template <class L, class W> VSR_HD uint64_t fp64_view8(const uint64_t* __restrict__ s8, const W& w, bool use_view) {
     static_assert(L::NW % 2 == 0, "whole 64-bit words");
     uint64_t fp = FP64_POLY;
     constexpr int full = L::VIEW_BITS >> 5, rem = L::VIEW_BITS & 31;
@@ -663,7 +663,7 @@ template <class L> VSR_HD uint64_t fp64_view8(const uint64_t* __restrict__ s8, c
     const int nw = use_view ? (full + (rem ? 1 : 0)) : L::NW;
     int i = 0;
     for (; i + 1 < nw; i += 2) {
-        uint32_t lo = w[i], hi = w[i + 1];
+        uint32_t lo = rdw(w, i), hi = rdw(w, i + 1);
         if (use_view && i + 1 == full) hi &= (1u << rem) - 1u;
         const uint64_t y = fp ^ (((uint64_t)hi << 32) | lo);
         fp = s8[7 * 256 + (y & 0xFF)] ^ s8[6 * 256 + ((y >> 8) & 0xFF)] ^ s8[5 * 256 + ((y >> 16) & 0xFF)] ^
@@ -671,7 +671,7 @@ template <class L> VSR_HD uint64_t fp64_view8(const uint64_t* __restrict__ s8, c
              s8[1 * 256 + ((y >> 48) & 0xFF)] ^ s8[(y >> 56) & 0xFF];
     }
     if (i < nw) { /* one trailing 32-bit word: four bytes */
-        uint32_t x = w[i];
+        uint32_t x = rdw(w, i);
         if (use_view && i == full) x &= (1u << rem) - 1u;
         const uint32_t y = x ^ (uint32_t)fp;
         fp = (fp >> 32) ^ s8[3 * 256 + (y & 0xFF)] ^ s8[2 * 256 + ((y >> 8) & 0xFF)] ^ s8[1 * 256 + ((y >> 16) & 0xFF)] ^ s8[(y >> 24) & 0xFF];

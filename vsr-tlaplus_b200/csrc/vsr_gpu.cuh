@@ -113,14 +113,14 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) { /* splitmix64 finaliser:
     x ^= x >> 31;
     return x;
 }
-template <class L> VSR_HD uint32_t check_hash(const uint32_t* w, bool use_view) {
+template <class L, class W> VSR_HD uint32_t check_hash(const W& w, bool use_view) {
     /* second, independent 32-bit hash of the VIEW words (3 instructions per word + finaliser): lets the seen-set tell
        fp64 collisions apart instead of silently merging two states as a bare fingerprint set would */
     constexpr int full = L::VIEW_BITS >> 5, rem = L::VIEW_BITS & 31;
     const int nw = use_view ? (full + (rem ? 1 : 0)) : L::NW;
     uint32_t h = 0x9747b28cu;
     for (int i = 0; i < nw; i++) {
-        uint32_t k = w[i];
+        uint32_t k = rdw(w, i);
         if (use_view && i == full) k &= (1u << rem) - 1u;
         h ^= k;
         h = ((h << 13) | (h >> 19)) * 5u + 0xe6546b64u;
@@ -274,7 +274,12 @@ template <class L> struct Expander {
     }
 
     /* fingerprint, route, insert, stage: the part of apply that does not depend on the action */
-    __device__ __noinline__ void emit(const uint32_t* n, int mult, int cand, int si, bool act) {
+    typedef SwzRow<L::NW> Row;
+    /* this lane's scratch row for the successor it builds: staging rows 32..63 are free whenever a batch starts
+       (fewer than 32 states are staged then), rotated by the lane so equal word indices fall in different banks */
+    __device__ __forceinline__ Row scratch() const { return Row{&S.stage[(32 + lane) * L::NW], lane % L::NW}; }
+
+    __device__ __noinline__ void emit(const Row n, int mult, int cand, int si, bool act) {
         bool isnew = false;
         int bad = 0;
         unsigned long long trec = 0;
@@ -307,7 +312,7 @@ template <class L> struct Expander {
                             rec.fp = fp; rec.parent = parent_gid; rec.auxkey = auxkey; rec.cand = (uint32_t)cand; rec.check = chk; rec._pad = 0;
                             uint8_t* dst = P.ties + t * (sizeof(TieRec) + L::BYTES);
                             *(TieRec*)dst = rec;
-                            for (int j = 0; j < L::NW; j++) ((uint32_t*)(dst + sizeof(TieRec)))[j] = n[j];
+                            for (int j = 0; j < L::NW; j++) ((uint32_t*)(dst + sizeof(TieRec)))[j] = rdw(n, j);
                         } else atomicExch(&P.ctr->overflow, 2);
                     }
                 } else if (P.sent_cache && P.sent_cache[mix64(fp ^ auxkey) & P.sent_mask] == (fp ^ ((uint64_t)auxkey << 40))) {
@@ -320,7 +325,7 @@ template <class L> struct Expander {
                     if (idx < P.send_cap) {
                         uint8_t* rec = P.send + ((size_t)owner * P.send_cap + idx) * (L::BYTES + sizeof(RecHdr));
                         uint32_t* rw = (uint32_t*)rec;
-                        for (int j = 0; j < L::NW; j++) rw[j] = n[j];
+                        for (int j = 0; j < L::NW; j++) rw[j] = rdw(n, j);
                         RecHdr* h = (RecHdr*)(rec + L::BYTES);
                         h->fp = fp; h->meta = meta; h->parent = parent_gid; h->cand = (uint32_t)cand; h->mult = (uint32_t)mult;
                     } else atomicExch(&P.ctr->overflow, 3);
@@ -329,9 +334,15 @@ template <class L> struct Expander {
         }
         /* compaction of the survivors into the warp's staging area (one ballot, all lanes) */
         const unsigned newmask = __ballot_sync(0xffffffffu, isnew);
+        /* the survivors' final rows may overlap other lanes' scratch rows: everybody reads first, then writes */
+        uint32_t v[L::NW];
+        if (isnew) {
+            for (int j = 0; j < L::NW; j++) v[j] = rdw(n, j);
+        }
+        __syncwarp();
         if (isnew) {
             const int slot = sn + __popc(newmask & ((1u << lane) - 1u));
-            for (int j = 0; j < L::NW; j++) S.stage[slot * L::NW + j] = n[j];
+            for (int j = 0; j < L::NW; j++) S.stage[slot * L::NW + j] = v[j];
             if (bad) {
                 trec |= 1ull << 63;
                 atomicOr(&P.ctr->viol_which, bad);
@@ -349,7 +360,7 @@ template <class L> struct Expander {
 #pragma unroll 1
         for (int cand = c0; cand < c1; cand++) {
             int m = 0;
-            if (have) m = O_::template step_grp<false, G>(P.run, mine, cand, nullptr);
+            if (have) m = O_::template step_grp<false, G>(P.run, mine, cand, (uint32_t*)nullptr);
             const unsigned en = __ballot_sync(0xffffffffu, m > 0);
             if (en) {
                 int base = 0;
@@ -362,7 +373,7 @@ template <class L> struct Expander {
                 const bool inl = m > 0 && pos >= Smem::QCAP;
                 if (m > 0 && !inl) B.pool[pos] = (uint16_t)(tid | ((cand - c0) << 9));
                 if (__any_sync(0xffffffffu, inl)) {
-                    uint32_t n[L::NW];
+                    const Row n = scratch();
                     int mult = 0;
                     if (inl) mult = O_::template step_grp<true, G>(P.run, mine, cand, n);
                     emit(n, mult, cand, tid, inl);
@@ -376,14 +387,14 @@ template <class L> struct Expander {
     }
     /* apply one batch of <= 32 pairs of group G */
     template <int G> __device__ __noinline__ void apply(int b, int k) {
-        uint32_t n[L::NW];
+        const Row n = scratch();
         int mult = 0, cand = 0, si = 0;
         const bool act = lane < k;
         if (act) {
             const unsigned item = B.pool[b + lane];
             si = item & 511;
             cand = O_::grp_begin(G) + (int)(item >> 9);
-            mult = O_::template step_grp<true, G>(P.run, &B.par[si * (L::NW + 1)], cand, n);
+            mult = O_::template step_grp<true, G>(P.run, (const uint32_t*)&B.par[si * (L::NW + 1)], cand, n);
         }
         emit(n, mult, cand, si, act);
     }
@@ -404,22 +415,30 @@ template <class L> struct Expander {
         if (P.check_deadlock && have && !any) atomicMin(&P.ctr->dead_id, P.in_base + first + tid);
         __syncthreads();
         /* batches: group g has ceil(|group g's pool segment| / 32) of them */
-        int nb[Smem::NG], gs[Smem::NG + 1], total = 0;
-        gs[0] = 0;
-        for (int g = 0; g < Smem::NG; g++) {
-            gs[g + 1] = gs[g] + B.qcount[g] < Smem::QCAP ? gs[g] + B.qcount[g] : Smem::QCAP;
-            nb[g] = (gs[g + 1] - gs[g] + 31) >> 5;
-            total += nb[g];
+        int total = 0;
+        {
+            int st = 0;
+            for (int g = 0; g < Smem::NG; g++) {
+                const int en = st + B.qcount[g] < Smem::QCAP ? st + B.qcount[g] : Smem::QCAP;
+                total += (en - st + 31) >> 5;
+                st = en;
+            }
         }
         for (;;) {
             int t = 0;
             if (lane == 0) t = atomicAdd(&B.take, 1);
             t = __shfl_sync(0xffffffffu, t, 0);
             if (t >= total) break;
-            int g = 0;
-            while (t >= nb[g]) { t -= nb[g]; g++; }
-            const int b = gs[g] + t * 32;
-            const int k = gs[g + 1] - b < 32 ? gs[g + 1] - b : 32;
+            int g = 0, st = 0, en = 0;
+            for (;; g++) { /* which group does batch t belong to, and where does that group's segment start */
+                en = st + B.qcount[g] < Smem::QCAP ? st + B.qcount[g] : Smem::QCAP;
+                const int nbg = (en - st + 31) >> 5;
+                if (t < nbg) break;
+                t -= nbg;
+                st = en;
+            }
+            const int b = st + t * 32;
+            const int k = en - b < 32 ? en - b : 32;
             switch (g) {
             case 0: apply<0>(b, k); break;   case 1: apply<1>(b, k); break;   case 2: apply<2>(b, k); break;
             case 3: apply<3>(b, k); break;   case 4: apply<4>(b, k); break;   case 5: apply<5>(b, k); break;

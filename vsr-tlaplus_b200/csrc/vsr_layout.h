@@ -144,15 +144,35 @@ template <int R_, int V_, int K_> struct Layout {
     static constexpr int NCAND = C_RNS + NGS;
 };
 
-/* --- element access (base, width compile-time; index run-time) */
-template <int B, int W> VSR_HD uint32_t fget(const uint32_t* w, int idx) {
-    const int b = B + idx * W;
-    return (w[b >> 5] >> (b & 31)) & ((1u << W) - 1u);
+/* --- word access.  A state is normally a plain word pointer; the expand kernel also builds successors in a
+   rotated shared-memory row (SwzRow) so that the 32 lanes of a warp, each owning one row, do not hit the same
+   banks.  Everything above this layer goes through rdw()/wrw(). */
+VSR_HD uint32_t rdw(const uint32_t* w, int i) { return w[i]; }
+VSR_HD void wrw(uint32_t* w, int i, uint32_t v) { w[i] = v; }
+template <int NW> struct SwzRow {
+    uint32_t* base; /* NW words */
+    int rot;        /* word i lives at base[(i + rot) mod NW] */
+};
+template <int NW> VSR_HD uint32_t rdw(const SwzRow<NW>& w, int i) {
+    int x = i + w.rot;
+    if (x >= NW) x -= NW;
+    return w.base[x];
 }
-template <int B, int W> VSR_HD void fset(uint32_t* w, int idx, uint32_t val) {
+template <int NW> VSR_HD void wrw(const SwzRow<NW>& w, int i, uint32_t v) {
+    int x = i + w.rot;
+    if (x >= NW) x -= NW;
+    w.base[x] = v;
+}
+
+/* --- element access (base, width compile-time; index run-time) */
+template <int B, int W, class S> VSR_HD uint32_t fget(const S& w, int idx) {
+    const int b = B + idx * W;
+    return (rdw(w, b >> 5) >> (b & 31)) & ((1u << W) - 1u);
+}
+template <int B, int W, class S> VSR_HD void fset(const S& w, int idx, uint32_t val) {
     const int b = B + idx * W;
     const uint32_t m = ((1u << W) - 1u) << (b & 31);
-    w[b >> 5] = (w[b >> 5] & ~m) | ((val << (b & 31)) & m);
+    wrw(w, b >> 5, (rdw(w, b >> 5) & ~m) | ((val << (b & 31)) & m));
 }
 #define VGET(Lt, F, w, i) ::vsr::fget<Lt::F##_B, Lt::F##_W>((w), (i))
 #define VSET(Lt, F, w, i, v) ::vsr::fset<Lt::F##_B, Lt::F##_W>((w), (i), (uint32_t)(v))
