@@ -191,6 +191,12 @@ constexpr int QPS = 10;       /* pool entries per parent state (pool = QPS * sta
 template <class L> struct WarpStage {
     alignas(16) uint32_t stage[SCAP * L::NW];    /* new states, packed back to back for the bulk store */
     unsigned long long tstage[SCAP];             /* their trace records */
+    /* per-warp running state.  It lives here, not in the Expander object: the big per-action routines are real calls
+       (one copy of each in the instruction cache), and an object whose address is passed to them would be kept in
+       local memory — 1024 threads x a few hundred bytes does not fit the L1 left beside 220 KB of shared memory. */
+    int sn;                                      /* states currently staged */
+    unsigned int coll, ties;
+    unsigned long long gen, probes;
 };
 template <class L, int WARPS> struct BlockSmemT {
     static constexpr int NS = WARPS * 32;        /* parent states per block round: one per thread */
@@ -228,9 +234,7 @@ template <class L> struct Expander {
     Smem& B;
     WarpStage<L>& S;
     const int lane, warp, tid;
-    int sn = 0, gbase = 0;
-    unsigned long long gen = 0;
-    unsigned probes = 0, coll = 0, ties = 0;
+    int gbase = 0;
     const uint32_t* mine = nullptr;
     bool have = false, any = false;
 
@@ -238,7 +242,8 @@ template <class L> struct Expander {
 
     /* flush the first n staged states (n <= 32) to the next frontier: one atomicAdd for the block of
        ids, one TMA bulk store for the states, then move the remainder (< 32 states) down */
-    __device__ __noinline__ void flush(int n) {
+    static __device__ __noinline__ void flush(const ExpandParams& P, WarpStage<L>& S, int lane, int n) {
+        const int sn = S.sn;
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(&P.ctr->out_count, (unsigned long long)n);
         base = __shfl_sync(0xffffffffu, base, 0);
@@ -269,7 +274,7 @@ template <class L> struct Expander {
         if (lane < rest) t = S.tstage[n + lane];
         __syncwarp();
         if (lane < rest) S.tstage[lane] = t;
-        sn = rest;
+        if (lane == 0) S.sn = rest;
         __syncwarp();
     }
 
@@ -277,9 +282,13 @@ template <class L> struct Expander {
     typedef SwzRow<L::NW> Row;
     /* this lane's scratch row for the successor it builds: staging rows 32..63 are free whenever a batch starts
        (fewer than 32 states are staged then), rotated by the lane so equal word indices fall in different banks */
-    __device__ __forceinline__ Row scratch() const { return Row{&S.stage[(32 + lane) * L::NW], lane % L::NW}; }
+    static __device__ __forceinline__ Row scratch(WarpStage<L>& S, int lane) { return Row{&S.stage[(32 + lane) * L::NW], lane % L::NW}; }
 
-    __device__ __noinline__ void emit(const Row n, int mult, int cand, int si, bool act) {
+    static __device__ __noinline__ void emit(const ExpandParams& P, Smem& B, WarpStage<L>& S, int lane, const Row n, int mult, int cand, int si,
+                                             bool act) {
+        unsigned long long gen = 0;
+        unsigned probes = 0, coll = 0, ties = 0;
+        int sn = S.sn;
         bool isnew = false;
         int bad = 0;
         unsigned long long trec = 0;
@@ -350,8 +359,26 @@ template <class L> struct Expander {
             S.tstage[slot] = trec;
         }
         sn += __popc(newmask);
+        /* per-warp totals of this batch */
+        for (int o = 16; o; o >>= 1) {
+            gen += __shfl_xor_sync(0xffffffffu, gen, o);
+            probes += __shfl_xor_sync(0xffffffffu, probes, o);
+            coll += __shfl_xor_sync(0xffffffffu, coll, o);
+            ties += __shfl_xor_sync(0xffffffffu, ties, o);
+        }
         __syncwarp();
-        while (sn >= 32) flush(32);
+        if (lane == 0) {
+            S.sn = sn;
+            S.gen += gen;
+            S.probes += probes;
+            S.coll += coll;
+            S.ties += ties;
+        }
+        __syncwarp();
+        while (sn >= 32) {
+            flush(P, S, lane, 32);
+            sn -= 32;
+        }
     }
 
     /* scan one action group: guards only; enabled pairs go to the block pool */
@@ -373,10 +400,10 @@ template <class L> struct Expander {
                 const bool inl = m > 0 && pos >= Smem::QCAP;
                 if (m > 0 && !inl) B.pool[pos] = (uint16_t)(tid | ((cand - c0) << 9));
                 if (__any_sync(0xffffffffu, inl)) {
-                    const Row n = scratch();
+                    const Row n = scratch(S, lane);
                     int mult = 0;
                     if (inl) mult = O_::template step_grp<true, G>(P.run, mine, cand, n);
-                    emit(n, mult, cand, tid, inl);
+                    emit(P, B, S, lane, n, mult, cand, tid, inl);
                 }
             }
         }
@@ -386,8 +413,8 @@ template <class L> struct Expander {
         gbase = gbase + B.qcount[G] < Smem::QCAP ? gbase + B.qcount[G] : Smem::QCAP;
     }
     /* apply one batch of <= 32 pairs of group G */
-    template <int G> __device__ __noinline__ void apply(int b, int k) {
-        const Row n = scratch();
+    template <int G> static __device__ __noinline__ void apply(const ExpandParams& P, Smem& B, WarpStage<L>& S, int lane, int b, int k) {
+        const Row n = scratch(S, lane);
         int mult = 0, cand = 0, si = 0;
         const bool act = lane < k;
         if (act) {
@@ -396,7 +423,7 @@ template <class L> struct Expander {
             cand = O_::grp_begin(G) + (int)(item >> 9);
             mult = O_::template step_grp<true, G>(P.run, (const uint32_t*)&B.par[si * (L::NW + 1)], cand, n);
         }
-        emit(n, mult, cand, si, act);
+        emit(P, B, S, lane, n, mult, cand, si, act);
     }
 
     __device__ void run_round(unsigned long long first, int count) {
@@ -440,40 +467,37 @@ template <class L> struct Expander {
             const int b = st + t * 32;
             const int k = en - b < 32 ? en - b : 32;
             switch (g) {
-            case 0: apply<0>(b, k); break;   case 1: apply<1>(b, k); break;   case 2: apply<2>(b, k); break;
-            case 3: apply<3>(b, k); break;   case 4: apply<4>(b, k); break;   case 5: apply<5>(b, k); break;
-            case 6: apply<6>(b, k); break;   case 7: apply<7>(b, k); break;   case 8: apply<8>(b, k); break;
-            case 9: apply<9>(b, k); break;   case 10: apply<10>(b, k); break; case 11: apply<11>(b, k); break;
-            default: apply<12>(b, k); break;
+            case 0: apply<0>(P, B, S, lane, b, k); break;   case 1: apply<1>(P, B, S, lane, b, k); break;   case 2: apply<2>(P, B, S, lane, b, k); break;
+            case 3: apply<3>(P, B, S, lane, b, k); break;   case 4: apply<4>(P, B, S, lane, b, k); break;   case 5: apply<5>(P, B, S, lane, b, k); break;
+            case 6: apply<6>(P, B, S, lane, b, k); break;   case 7: apply<7>(P, B, S, lane, b, k); break;   case 8: apply<8>(P, B, S, lane, b, k); break;
+            case 9: apply<9>(P, B, S, lane, b, k); break;   case 10: apply<10>(P, B, S, lane, b, k); break; case 11: apply<11>(P, B, S, lane, b, k); break;
+            default: apply<12>(P, B, S, lane, b, k); break;
             }
         }
     }
 
     __device__ void finish() {
-        while (sn > 0) flush(sn < 32 ? sn : 32);
-        /* per-warp totals */
-        for (int o = 16; o; o >>= 1) {
-            gen += __shfl_xor_sync(0xffffffffu, gen, o);
-            probes += __shfl_xor_sync(0xffffffffu, probes, o);
-            coll += __shfl_xor_sync(0xffffffffu, coll, o);
-            ties += __shfl_xor_sync(0xffffffffu, ties, o);
-        }
+        while (S.sn > 0) flush(P, S, lane, S.sn < 32 ? S.sn : 32);
         if (lane == 0) {
-            atomicAdd(&P.ctr->generated, gen);
-            atomicAdd(&P.ctr->probes, (unsigned long long)probes);
-            if (coll) atomicAdd(&P.ctr->collisions, (unsigned long long)coll);
-            if (ties) atomicAdd(&P.ctr->ties, (unsigned long long)ties);
+            atomicAdd(&P.ctr->generated, S.gen);
+            atomicAdd(&P.ctr->probes, S.probes);
+            if (S.coll) atomicAdd(&P.ctr->collisions, (unsigned long long)S.coll);
+            if (S.ties) atomicAdd(&P.ctr->ties, (unsigned long long)S.ties);
         }
     }
 };
 
-template <class L> __global__ void __launch_bounds__(ExpandCfg<L>::WARPS * 32, 2) expand_kernel(const ExpandParams P) {
+template <class L> __global__ void __launch_bounds__(ExpandCfg<L>::WARPS * 32, 2) expand_kernel(const __grid_constant__ ExpandParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     typedef typename ExpandCfg<L>::Smem Smem;
     Smem& B = *reinterpret_cast<Smem*>(smem_raw);
     for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) B.fp_tab[i] = P.fp_tab[i];
     __shared__ unsigned long long next_round;
     Expander<L> X(P, B);
+    if ((threadIdx.x & 31) == 0) {
+        WarpStage<L>& S = B.w[threadIdx.x >> 5];
+        S.sn = 0; S.coll = 0; S.ties = 0; S.gen = 0; S.probes = 0;
+    }
     const unsigned long long nrounds = (P.n_in + Smem::NS - 1) / Smem::NS;
     if (threadIdx.x == 0) next_round = atomicAdd(&P.ctr->work_next, 1ull);
     for (;;) {
