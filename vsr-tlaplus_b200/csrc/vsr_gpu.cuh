@@ -400,10 +400,7 @@ template <class L> struct Expander {
                 const bool inl = m > 0 && pos >= Smem::QCAP;
                 if (m > 0 && !inl) B.pool[pos] = (uint16_t)(tid | ((cand - c0) << 9));
                 if (__any_sync(0xffffffffu, inl)) {
-                    const Row n = scratch(S, lane);
-                    int mult = 0;
-                    if (inl) mult = O_::template step_grp<true, G>(P.run, mine, cand, n);
-                    emit(P, B, S, lane, n, mult, cand, tid, inl);
+                    apply<G>(P, B, S, lane, mine, cand, tid, inl);
                 }
             }
         }
@@ -412,18 +409,24 @@ template <class L> struct Expander {
         __syncthreads();
         gbase = gbase + B.qcount[G] < Smem::QCAP ? gbase + B.qcount[G] : Smem::QCAP;
     }
-    /* apply one batch of <= 32 pairs of group G */
-    template <int G> static __device__ __noinline__ void apply(const ExpandParams& P, Smem& B, WarpStage<L>& S, int lane, int b, int k) {
+    /* apply one (parent, candidate) pair of group G per lane; the only copy of that action's effect in the kernel */
+    template <int G> static __device__ __noinline__ void apply(const ExpandParams& P, Smem& B, WarpStage<L>& S, int lane, const uint32_t* parent,
+                                                               int cand, int si, bool act) {
         const Row n = scratch(S, lane);
-        int mult = 0, cand = 0, si = 0;
+        int mult = 0;
+        if (act) mult = O_::template step_grp<true, G>(P.run, parent, cand, n);
+        emit(P, B, S, lane, n, mult, cand, si, act);
+    }
+    /* one batch of <= 32 queued pairs of group G, pool[b .. b + k) */
+    template <int G> static __device__ __forceinline__ void batch(const ExpandParams& P, Smem& B, WarpStage<L>& S, int lane, int b, int k) {
         const bool act = lane < k;
+        int cand = 0, si = 0;
         if (act) {
             const unsigned item = B.pool[b + lane];
             si = item & 511;
             cand = O_::grp_begin(G) + (int)(item >> 9);
-            mult = O_::template step_grp<true, G>(P.run, (const uint32_t*)&B.par[si * (L::NW + 1)], cand, n);
         }
-        emit(P, B, S, lane, n, mult, cand, si, act);
+        apply<G>(P, B, S, lane, &B.par[si * (L::NW + 1)], cand, si, act);
     }
 
     __device__ void run_round(unsigned long long first, int count) {
@@ -467,11 +470,11 @@ template <class L> struct Expander {
             const int b = st + t * 32;
             const int k = en - b < 32 ? en - b : 32;
             switch (g) {
-            case 0: apply<0>(P, B, S, lane, b, k); break;   case 1: apply<1>(P, B, S, lane, b, k); break;   case 2: apply<2>(P, B, S, lane, b, k); break;
-            case 3: apply<3>(P, B, S, lane, b, k); break;   case 4: apply<4>(P, B, S, lane, b, k); break;   case 5: apply<5>(P, B, S, lane, b, k); break;
-            case 6: apply<6>(P, B, S, lane, b, k); break;   case 7: apply<7>(P, B, S, lane, b, k); break;   case 8: apply<8>(P, B, S, lane, b, k); break;
-            case 9: apply<9>(P, B, S, lane, b, k); break;   case 10: apply<10>(P, B, S, lane, b, k); break; case 11: apply<11>(P, B, S, lane, b, k); break;
-            default: apply<12>(P, B, S, lane, b, k); break;
+            case 0: batch<0>(P, B, S, lane, b, k); break;   case 1: batch<1>(P, B, S, lane, b, k); break;   case 2: batch<2>(P, B, S, lane, b, k); break;
+            case 3: batch<3>(P, B, S, lane, b, k); break;   case 4: batch<4>(P, B, S, lane, b, k); break;   case 5: batch<5>(P, B, S, lane, b, k); break;
+            case 6: batch<6>(P, B, S, lane, b, k); break;   case 7: batch<7>(P, B, S, lane, b, k); break;   case 8: batch<8>(P, B, S, lane, b, k); break;
+            case 9: batch<9>(P, B, S, lane, b, k); break;   case 10: batch<10>(P, B, S, lane, b, k); break; case 11: batch<11>(P, B, S, lane, b, k); break;
+            default: batch<12>(P, B, S, lane, b, k); break;
             }
         }
     }
