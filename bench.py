@@ -275,6 +275,8 @@ def main():
             "gpu_launches": launches0,
             "kernel_seconds": kern_s,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "traffic_note": "launches differ in size, so no single per-launch figure: the ncu --set full capture of two mid-size "
+                                         "wavefronts (profiles/round1_expand_kernel.md) measured dram read+write = 1.58x the algorithmic bytes",
                          "peak_source": peak_src, "bytes_per_state": b_alg, "g": g,
                          "kernel": "expand_kernel<Layout<3,2,3>> (per-GPU states x B_alg / sum of per-level kernel time, max over ranks)"},
             "e2e": {"value": e2e_states / e2e_s, "unit": "states/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
