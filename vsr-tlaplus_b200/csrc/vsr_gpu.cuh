@@ -289,6 +289,8 @@ template <class L> struct Expander {
         unsigned long long gen = 0;
         unsigned probes = 0, coll = 0, ties = 0;
         int sn = S.sn;
+        int send_to = -1;
+        uint64_t s_fp = 0, s_meta = 0, s_parent = 0;
         bool isnew = false;
         int bad = 0;
         unsigned long long trec = 0;
@@ -330,15 +332,29 @@ template <class L> struct Expander {
                     gen += (unsigned long long)mult;
                 } else {
                     if (P.sent_cache) P.sent_cache[mix64(fp ^ auxkey) & P.sent_mask] = fp ^ ((uint64_t)auxkey << 40);
-                    const unsigned idx = atomicAdd(&P.send_count[owner], 1u);
-                    if (idx < P.send_cap) {
-                        uint8_t* rec = P.send + ((size_t)owner * P.send_cap + idx) * (L::BYTES + sizeof(RecHdr));
-                        uint32_t* rw = (uint32_t*)rec;
-                        for (int j = 0; j < L::NW; j++) rw[j] = rdw(n, j);
-                        RecHdr* h = (RecHdr*)(rec + L::BYTES);
-                        h->fp = fp; h->meta = meta; h->parent = parent_gid; h->cand = (uint32_t)cand; h->mult = (uint32_t)mult;
-                    } else atomicExch(&P.ctr->overflow, 3);
+                    send_to = owner;
+                    s_fp = fp; s_meta = meta; s_parent = parent_gid;
                 }
+            }
+        }
+        /* records for peers: the lanes of this batch that send to the same rank take their slots with ONE atomicAdd
+           (a per-record atomic on `world` hot counters serialises the whole GPU) */
+        if (P.world > 1) {
+            const unsigned senders = __ballot_sync(0xffffffffu, send_to >= 0);
+            if (send_to >= 0) {
+                const unsigned peers = __match_any_sync(senders, send_to);
+                const int leader = __ffs(peers) - 1;
+                unsigned base = 0;
+                if (lane == leader) base = atomicAdd(&P.send_count[send_to], (unsigned)__popc(peers));
+                base = __shfl_sync(peers, base, leader);
+                const unsigned idx = base + __popc(peers & ((1u << lane) - 1u));
+                if (idx < P.send_cap) {
+                    uint8_t* rec = P.send + ((size_t)send_to * P.send_cap + idx) * (L::BYTES + sizeof(RecHdr));
+                    uint32_t* rw = (uint32_t*)rec;
+                    for (int j = 0; j < L::NW; j++) rw[j] = rdw(n, j);
+                    RecHdr* h = (RecHdr*)(rec + L::BYTES);
+                    h->fp = s_fp; h->meta = s_meta; h->parent = s_parent; h->cand = (uint32_t)cand; h->mult = (uint32_t)mult;
+                } else atomicExch(&P.ctr->overflow, 3);
             }
         }
         /* compaction of the survivors into the warp's staging area (one ballot, all lanes) */
