@@ -186,6 +186,22 @@ int vsr_engine_build_trace(VsrEngine* e, uint64_t local_id, void* trace_out, uin
 int vsr_replay_candidates(const VsrModel* m, const uint32_t* cands, int n, void* trace_out, uint8_t* trace_actions,
                           size_t trace_cap);
 
+/* ---- simulation mode: TLC `-simulate [-depth N]` (the reference's README.md:22 recommends it for the defect).
+ * num_walks random behaviours from Init of at most `depth` states (TLC's default 100), uniformly random among the
+ * enabled (action, binding) pairs at every step, invariant checked on every state; one GPU thread per walk.  Returns 12
+ * and the violating behaviour (literal value names, re-walked on the host) if one walk hits a violation. */
+typedef struct VsrSimOpts {
+    int32_t device, depth;
+    uint64_t num_walks, seed;
+} VsrSimOpts;
+typedef struct VsrSimStats {
+    uint64_t walks, steps, dead_ends, violating_walk;
+    int32_t rc, violation_depth, trace_len, _pad;
+    double kernel_ms, seconds_total;
+} VsrSimStats;
+int vsr_simulate(const VsrModel* m, const VsrSimOpts* opts, VsrSimStats* out, void* trace_out, uint8_t* trace_actions,
+                 size_t trace_cap);
+
 /* seen-set micro-benchmark: inserts n splitmix64 keys (a fraction dup_frac of them repeats) into a fresh
  * table of `capacity` slots (power of two) with the BFS's own insert routine; best of `iters` launches.
  * out[0] = device ms per launch, out[1] = keys found new (must equal the number of distinct keys), out[2] = slots probed. */

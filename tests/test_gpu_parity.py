@@ -192,3 +192,34 @@ def test_view_ties_resolve_to_smallest_aux_key(pkg):
         assert eng.trace_record(1) == (0, 101)                 # ... with the trace record of the winner
     finally:
         eng.close()
+
+
+def test_simulation_mode_finds_and_replays_a_violation(pkg):
+    """TLC's `-simulate` (the reference's README recommends it for the defect): random walks on the GPU.  With
+    AcknowledgedWritesExistOnMajority on (R=3, V=2, L=1) violations are frequent; the violating walk is re-walked on the host
+    and must be a literal behaviour of the spec per the ORACLE, ending in a state the oracle's invariant rejects."""
+    inv = ("AcknowledgedWritesExistOnMajority",)
+    mc = pkg.ModelChecker.from_constants(3, 2, 1, invariants=inv)
+    st, trace = mc.simulate(num_walks=1 << 18, depth=60, seed=7)
+    assert st.rc == 12 and st.walks == 1 << 18 and st.steps > 0
+    assert len(trace) == st.violation_depth and trace[0][0] == "Initial predicate"
+    q = orc.params(3, 2, 1, symmetry=False, invariant=2)
+    L = orc.lib()
+    flats = [mc.unpack(s) for _, s in trace]
+    for i in range(len(flats) - 1):
+        cap = 256
+        succ = (pkg.checker.VsrFlatState * cap)()
+        acts = (C.c_int * cap)()
+        n = L.orc_successors_flat(q, C.byref(flats[i]), succ, acts, cap)
+        want = orc.digests_full_of(q, (pkg.checker.VsrFlatState * 1)(flats[i + 1]))[0]
+        got = orc.digests_full_of(q, succ)[:n]
+        assert any(g == want and pkg.ACTION_NAMES[acts[k]] == trace[i + 1][0] for k, g in enumerate(got)), f"step {i + 1}"
+    assert L.orc_invariant_flat(q, C.byref(flats[-1])) == 0
+    # same seed, same answer; other seed, (almost surely) another walk
+    st2, trace2 = mc.simulate(num_walks=1 << 18, depth=60, seed=7)
+    assert (st2.violating_walk, st2.violation_depth, st2.steps) == (st.violating_walk, st.violation_depth, st.steps)
+    assert [s for _, s in trace2] == [s for _, s in trace]
+    # no violation where there is none (AcknowledgedWriteNotLost holds on R=2)
+    ok = pkg.ModelChecker.from_constants(2, 2, 2)
+    st3, trace3 = ok.simulate(num_walks=1 << 16, depth=40, seed=3)
+    assert st3.rc == 0 and trace3 == [] and st3.dead_ends > 0

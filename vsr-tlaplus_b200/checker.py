@@ -113,6 +113,16 @@ class VsrStats(C.Structure):
     ]
 
 
+class VsrSimOpts(C.Structure):
+    _fields_ = [("device", C.c_int32), ("depth", C.c_int32), ("num_walks", C.c_uint64), ("seed", C.c_uint64)]
+
+
+class VsrSimStats(C.Structure):
+    _fields_ = [("walks", C.c_uint64), ("steps", C.c_uint64), ("dead_ends", C.c_uint64), ("violating_walk", C.c_uint64),
+                ("rc", C.c_int32), ("violation_depth", C.c_int32), ("trace_len", C.c_int32), ("_pad", C.c_int32),
+                ("kernel_ms", C.c_double), ("seconds_total", C.c_double)]
+
+
 class VsrLevelInfo(C.Structure):
     _fields_ = [
         ("new_states", C.c_uint64), ("generated", C.c_uint64), ("frontier_in", C.c_uint64), ("ties", C.c_uint64),
@@ -129,7 +139,7 @@ EXPORTED_SYMBOLS = [
     "vsr_engine_record_bytes", "vsr_engine_set_send_buffers", "vsr_engine_seed_init", "vsr_engine_expand", "vsr_engine_expand_part",
     "vsr_engine_insert_records", "vsr_engine_finish_level", "vsr_engine_frontier_size", "vsr_engine_read_frontier",
     "vsr_engine_trace_record", "vsr_engine_stats", "vsr_engine_reset", "vsr_engine_lookup", "vsr_engine_last_error", "vsr_engine_collected", "vsr_engine_build_trace",
-    "vsr_replay_candidates", "vsr_probe_bench", "vsr_version",
+    "vsr_replay_candidates", "vsr_probe_bench", "vsr_simulate", "vsr_version",
 ]
 
 _lib = None
@@ -192,6 +202,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.vsr_engine_collected.restype = u64
     lib.vsr_engine_build_trace.argtypes = [vp, u64, vp, C.POINTER(C.c_uint8), C.c_size_t]
     lib.vsr_replay_candidates.argtypes = [vp, C.POINTER(C.c_uint32), C.c_int, vp, C.POINTER(C.c_uint8), C.c_size_t]
+    lib.vsr_simulate.argtypes = [vp, C.POINTER(VsrSimOpts), C.POINTER(VsrSimStats), vp, C.POINTER(C.c_uint8), C.c_size_t]
     lib.vsr_probe_bench.argtypes = [C.c_int, u64, u64, C.c_double, C.c_int, C.POINTER(C.c_double)]
     if path is None:
         _lib = lib
@@ -441,6 +452,20 @@ class ModelChecker:
         sb = self.state_bytes
         trace = [(ACTION_NAMES[acts[i]], raw[i * sb:(i + 1) * sb]) for i in range(int(st.trace_len))]
         return self.result_from_stats(st, rc, trace)
+
+    def simulate(self, num_walks: int = 1 << 20, depth: int = 100, seed: int = 1, device: int = 0):
+        """TLC's `-simulate -depth N`: random behaviours on the GPU.  Returns (VsrSimStats, trace) — the trace is the
+        violating behaviour [(action name, packed state)] when rc == 12, else []."""
+        o = VsrSimOpts(device=device, depth=depth, num_walks=num_walks, seed=seed)
+        st = VsrSimStats()
+        cap = max(depth + 1, 2)
+        tr = self._buf(cap)
+        acts = (C.c_uint8 * cap)()
+        rc = self._lib.vsr_simulate(self._h, C.byref(o), C.byref(st), tr, acts, cap)
+        if rc == 153:
+            raise VsrError(rc, "no usable CUDA device: simulation runs on the GPU only")
+        raw, sb = bytes(tr), self.state_bytes
+        return st, [(ACTION_NAMES[acts[i]], raw[i * sb:(i + 1) * sb]) for i in range(int(st.trace_len))]
 
     def _check_stepwise(self, **kw) -> CheckResult:
         """Same BFS pumped level by level through the engine entry points (keeps every level for tests)."""

@@ -550,6 +550,25 @@ template <class L> struct Ops {
         return x < nc ? L::C_SGS + order[x] * O * O + c % (O * O) : -1;
     }
 
+    /* Simulation mode (TLC `-simulate`, README.md:22 of the reference): one step of a random walk.  Picks uniformly among
+       the enabled (action, binding) candidates by reservoir sampling — one pass, one draw per enabled candidate — so host
+       and device walk identically for the same generator state.  Returns the chosen candidate, -1 if none is enabled. */
+    static VSR_HD uint64_t rng_next(uint64_t& x) { /* splitmix64 */
+        uint64_t z = (x += 0x9E3779B97F4A7C15ULL);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        return z ^ (z >> 31);
+    }
+    static VSR_HD int random_enabled(const RunCfg& run, const uint32_t* s, uint64_t& rng) {
+        int chosen = -1, n = 0;
+        for (int cand = 0; cand < L::NCAND; cand++) {
+            if (step<false>(run, s, cand, (uint32_t*)nullptr) <= 0) continue;
+            n++;
+            if (rng_next(rng) % (uint64_t)n == 0) chosen = cand;
+        }
+        return chosen;
+    }
+
     /* General canonicalisation under SYMMETRY for an arbitrarily labelled packed state: relabel the
        created values in (view, op_number) order of their Prepare.  step() keeps states canonical
        incrementally; this is for pack() and for tests.  Returns 0 or E_PREPKEY_CLASH. */

@@ -26,11 +26,14 @@ static void usage() {
             "  -gpu N               CUDA device ordinal (default 0)\n"
             "  -table N / -frontier N   seen-set slots / states per frontier buffer (default: from free memory)\n"
             "  -continue            keep exploring after the first violation\n"
+            "  -simulate [-num W] [-seed S]   TLC's simulation mode: W random behaviours of at most -depth (default 100) states\n"
             "  -notrace             do not keep parent records (no counterexample)\n");
 }
 
 int main(int argc, char** argv) {
     const char *cfg = nullptr, *tla = nullptr, *dump = nullptr;
+    bool simulate = false;
+    unsigned long long sim_walks = 1ull << 22, sim_seed = 1;
     VsrRunOpts o;
     memset(&o, 0, sizeof o);
     o.check_deadlock = 1; /* TLC's default */
@@ -53,6 +56,9 @@ int main(int argc, char** argv) {
         else if (a == "-table" && i + 1 < argc) o.table_capacity = strtoull(argv[++i], 0, 10);
         else if (a == "-frontier" && i + 1 < argc) o.frontier_capacity = strtoull(argv[++i], 0, 10);
         else if (a == "-continue") o.stop_on_violation = 0;
+        else if (a == "-simulate") simulate = true;
+        else if (a == "-num" && i + 1 < argc) sim_walks = strtoull(argv[++i], 0, 10);
+        else if (a == "-seed" && i + 1 < argc) sim_seed = strtoull(argv[++i], 0, 10);
         else if (a == "-notrace") o.keep_trace = 0;
         else if (a == "-h" || a == "-help" || a == "--help") { usage(); return 0; }
         else if (a[0] != '-') tla = argv[i];
@@ -70,12 +76,26 @@ int main(int argc, char** argv) {
            info.replica_count, info.client_count, info.value_count, info.start_view_on_timer_limit, info.restart_empty_limit,
            info.view ? " VIEW view" : "", info.symmetry ? " SYMMETRY symmValues" : "", info.state_bytes, info.state_bits, info.num_candidates);
     if (tla) printf("Spec %s verified as MODULE VSR (hash %016llx)\n", tla, (unsigned long long)info.spec_hash);
-    printf("Running breadth-first search Model-Checking with fp 0 on GPU %d.\n", o.device);
     VsrStats st;
+    memset(&st, 0, sizeof st);
     const size_t tcap = 512;
     std::vector<unsigned char> trace(tcap * (size_t)info.state_bytes);
     std::vector<uint8_t> acts(tcap);
-    rc = vsr_bfs(m, &o, &st, trace.data(), acts.data(), tcap);
+    VsrSimStats sim;
+    memset(&sim, 0, sizeof sim);
+    if (simulate) {
+        VsrSimOpts so;
+        so.device = o.device;
+        so.depth = o.max_depth > 0 ? o.max_depth : 100;
+        so.num_walks = sim_walks;
+        so.seed = sim_seed;
+        printf("Running Random Simulation with seed %llu: %llu behaviours of at most %d states on GPU %d.\n", sim_seed, sim_walks, so.depth, o.device);
+        rc = vsr_simulate(m, &so, &sim, trace.data(), acts.data(), tcap);
+        st.trace_len = sim.trace_len;
+    } else {
+        printf("Running breadth-first search Model-Checking with fp 0 on GPU %d.\n", o.device);
+        rc = vsr_bfs(m, &o, &st, trace.data(), acts.data(), tcap);
+    }
     if (rc == VSR_RC_VIOLATION || rc == VSR_RC_DEADLOCK) {
         if (rc == VSR_RC_VIOLATION) printf("Error: Invariant %s is violated.\n", (info.invariant & 1) ? "AcknowledgedWriteNotLost" : "AcknowledgedWritesExistOnMajority");
         else printf("Error: Deadlock reached.\n");
@@ -101,6 +121,13 @@ int main(int argc, char** argv) {
         fprintf(stderr, "Error: run failed with status %d (device error code %d)\n", rc, st.error_code);
     } else if (st.complete) {
         printf("Model checking completed. No error has been found.\n");
+    }
+    if (simulate) {
+        printf("%llu behaviours, %llu states checked (%llu ended in a state without successors); %.3f s, %.0f states/s.\n",
+               (unsigned long long)sim.walks, (unsigned long long)(sim.steps + sim.walks), (unsigned long long)sim.dead_ends, sim.seconds_total,
+               (sim.steps + sim.walks) / (sim.kernel_ms > 0 ? sim.kernel_ms / 1e3 : 1));
+        vsr_model_free(m);
+        return rc;
     }
     printf("%llu states generated, %llu distinct states found, %llu states left on queue.\n", (unsigned long long)st.generated,
            (unsigned long long)st.distinct, (unsigned long long)st.queue);

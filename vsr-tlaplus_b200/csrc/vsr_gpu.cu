@@ -28,6 +28,7 @@ struct GpuOps {
     cudaError_t (*launch_patch)(const ExpandParams&, const uint8_t* ties, unsigned long long ntie, unsigned long long n_out, cudaStream_t);
     int tie_bytes;
     cudaError_t (*prepare)(int* blocks_per_sm);
+    cudaError_t (*launch_simulate)(const SimParams&, int grid, cudaStream_t);
 };
 
 template <class L> struct GpuThunks {
@@ -51,10 +52,14 @@ template <class L> struct GpuThunks {
         patch_ties_kernel<L><<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(p, ties, ntie, n_out);
         return cudaGetLastError();
     }
+    static cudaError_t launch_simulate(const SimParams& q, int grid, cudaStream_t st) {
+        simulate_kernel<L><<<grid, 128, 0, st>>>(q);
+        return cudaGetLastError();
+    }
     static uint32_t chk(const uint32_t* w, int use_view) { return check_hash<L>(w, use_view != 0); }
     static const GpuOps* get() {
         static const GpuOps ops = {chk, L::R, L::V, L::K, L::NW, L::BYTES, (int)(L::BYTES + sizeof(RecHdr)), sizeof(typename ExpandCfg<L>::Smem), ExpandCfg<L>::WARPS * 32,
-                                   launch_expand, launch_insert, launch_patch, (int)(sizeof(TieRec) + L::BYTES), prepare};
+                                   launch_expand, launch_insert, launch_patch, (int)(sizeof(TieRec) + L::BYTES), prepare, launch_simulate};
         return &ops;
     }
 };
@@ -590,6 +595,76 @@ int vsr_bfs(const VsrModel* m, const VsrRunOpts* opts, VsrStats* stats, void* tr
     if (rc && opts->verbose) fprintf(stderr, "vsr_bfs: %s\n", e->last_error);
     vsr_engine_destroy(e);
     return result;
+}
+
+/* TLC `-simulate`: random walks on the GPU; a violating walk is re-walked on the host (same generator, same step
+   function) and returned as a literal behaviour. */
+int vsr_simulate(const VsrModel* m, const VsrSimOpts* o, VsrSimStats* out, void* trace_out, uint8_t* trace_actions, size_t trace_cap) {
+    if (!m || !o || !out) return VSR_RC_ERROR;
+    memset(out, 0, sizeof *out);
+    if (!m->gpu) return VSR_RC_CONFIG_ERROR;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return VSR_RC_SYSTEM;
+    if (cudaSetDevice(o->device) != cudaSuccess) return VSR_RC_SYSTEM;
+    const double t0 = now_s();
+    unsigned long long* d = nullptr;
+    if (cudaMalloc(&d, 24) != cudaSuccess) return VSR_RC_SYSTEM;
+    unsigned long long init[3] = {~0ull, 0, 0};
+    cudaMemcpy(d, init, 24, cudaMemcpyHostToDevice);
+    SimParams q;
+    q.num_walks = o->num_walks;
+    q.seed = o->seed;
+    q.depth = o->depth > 0 ? o->depth : 100; /* TLC's default simulation depth */
+    q.run = m->run;
+    q.first_bad = d;
+    q.steps = d + 1;
+    q.dead_ends = d + 2;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, o->device);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a);
+    cudaError_t ce = m->gpu->launch_simulate(q, prop.multiProcessorCount * 16, 0);
+    cudaEventRecord(b);
+    if (ce != cudaSuccess || cudaEventSynchronize(b) != cudaSuccess) { cudaFree(d); return VSR_RC_SYSTEM; }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    unsigned long long h[3];
+    cudaMemcpy(h, d, 24, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    out->walks = o->num_walks;
+    out->steps = h[1];
+    out->dead_ends = h[2];
+    out->kernel_ms = ms;
+    int rc = 0;
+    if (h[0] != ~0ull) {
+        rc = VSR_RC_VIOLATION;
+        out->violating_walk = h[0] >> 16;
+        out->violation_depth = (int)(h[0] & 0xFFFF);
+        /* re-walk on the host */
+        const ModelOps* ops = m->ops;
+        std::vector<uint32_t> cands;
+        uint32_t cur[VSR_MAX_STATE_BYTES / 4], nxt[VSR_MAX_STATE_BYTES / 4];
+        ops->init(cur);
+        uint64_t rng = o->seed ^ (out->violating_walk * 0xD1B54A32D192ED03ULL);
+        for (int dd = 2; dd <= out->violation_depth; dd++) {
+            const int c = ops->random_enabled(&m->run, cur, &rng);
+            if (c < 0 || ops->step(&m->run, cur, c, nxt) <= 0) { rc = VSR_RC_ERROR; break; }
+            memcpy(cur, nxt, ops->bytes);
+            cands.push_back((uint32_t)c);
+        }
+        if (rc == VSR_RC_VIOLATION && !ops->invariant(&m->run, cur)) rc = VSR_RC_ERROR; /* host and device disagree */
+        if (rc == VSR_RC_VIOLATION && trace_out) {
+            const int n = vsr_replay_candidates(m, cands.data(), (int)cands.size(), trace_out, trace_actions, trace_cap);
+            out->trace_len = n > 0 ? n : 0;
+        }
+    }
+    out->rc = rc;
+    out->seconds_total = now_s() - t0;
+    return rc;
 }
 
 int vsr_probe_bench(int device, uint64_t capacity, uint64_t n, double dup_frac, int iters, double* ms_out) {

@@ -649,6 +649,45 @@ __global__ void lookup_kernel(const uint64_t* table, unsigned long long mask, ui
     *meta_out = 0;
 }
 
+/* ------------------------------------------------------------------ simulation mode (TLC `-simulate`)
+   One thread per random walk from Init, `depth` states long at most; the invariant is checked on every state reached.
+   The first violating (walk, depth) is kept (smallest walk index wins) and re-walked on the host for the trace. */
+struct SimParams {
+    unsigned long long num_walks, seed;
+    int depth;
+    RunCfg run;
+    unsigned long long* first_bad; /* walk << 16 | depth of the state that violates (~0 = none) */
+    unsigned long long* steps;     /* transitions taken */
+    unsigned long long* dead_ends; /* walks that stopped in a state without successors */
+};
+template <class L> __global__ void simulate_kernel(const SimParams Q) {
+    unsigned long long steps = 0, dead = 0;
+    for (unsigned long long wk = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; wk < Q.num_walks; wk += (unsigned long long)gridDim.x * blockDim.x) {
+        uint64_t rng = Q.seed ^ (wk * 0xD1B54A32D192ED03ULL);
+        uint32_t a[L::NW], b[L::NW];
+        Ops<L>::init((uint32_t*)a);
+        for (int d = 2; d <= Q.depth; d++) {
+            const int cand = Ops<L>::random_enabled(Q.run, (const uint32_t*)a, rng);
+            if (cand < 0) { dead++; break; }
+            if (Ops<L>::template step<true>(Q.run, (const uint32_t*)a, cand, (uint32_t*)b) <= 0) break;
+            for (int j = 0; j < L::NW; j++) a[j] = b[j];
+            steps++;
+            if (Ops<L>::invariant(Q.run, (const uint32_t*)a)) {
+                atomicMin(Q.first_bad, (wk << 16) | (unsigned long long)d);
+                break;
+            }
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        steps += __shfl_xor_sync(0xffffffffu, steps, o);
+        dead += __shfl_xor_sync(0xffffffffu, dead, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(Q.steps, steps);
+        atomicAdd(Q.dead_ends, dead);
+    }
+}
+
 /* seen-set micro-benchmark: n splitmix64 keys, a fraction of them duplicates, inserted with the same
    table_insert the BFS uses; nothing else in the loop, so its rate is the random-probe ceiling of this table design */
 __global__ void probe_bench_kernel(uint64_t* table, unsigned long long mask, unsigned long long n, unsigned long long distinct,

@@ -29,6 +29,7 @@ template <class L> struct Thunks {
     static int action_of(int cand) { return Ops<L>::action_of(cand); }
     static int invariant(const RunCfg* run, const uint32_t* w) { return Ops<L>::invariant(*run, w); }
     static uint64_t fingerprint(const uint32_t* w, int use_view) { return fp64_view8<L>(fp64_table(), w, use_view != 0); }
+    static int random_enabled(const RunCfg* run, const uint32_t* s, uint64_t* rng) { return Ops<L>::random_enabled(*run, s, *rng); }
     static uint64_t fingerprint_bytewise(const uint32_t* w, int use_view) { return fp64_view<L>(fp64_table(), w, use_view != 0); }
     static uint32_t aux_key(const uint32_t* w) { return Ops<L>::aux_key(w); }
     static int canon(uint32_t* w) { return Ops<L>::canonicalize(w); }
@@ -37,7 +38,7 @@ template <class L> struct Thunks {
     static int literal_cand(const uint32_t* w, int cand) { return Ops<L>::literal_cand(w, cand); }
     static const ModelOps* get() {
         static const ModelOps ops = {L::R, L::V, L::K, L::NW, L::BYTES, L::TOTAL_BITS, L::NCAND, init, step, guard,
-                                     action_of, invariant, fingerprint, aux_key, canon, unpack, pack, literal_cand, fingerprint_bytewise};
+                                     action_of, invariant, fingerprint, aux_key, canon, unpack, pack, literal_cand, fingerprint_bytewise, random_enabled};
         return &ops;
     }
 };

@@ -33,6 +33,7 @@ struct ModelOps {
     int (*pack)(const VsrFlatState*, uint32_t*, int symmetry);
     int (*literal_cand)(const uint32_t*, int cand);
     uint64_t (*fingerprint_bytewise)(const uint32_t*, int use_view);
+    int (*random_enabled)(const RunCfg*, const uint32_t*, uint64_t* rng);
 };
 const ModelOps* find_model_ops(int R, int V, int K);
 const GpuOps* find_gpu_ops(int R, int V, int K); /* defined in vsr_gpu.cu */
