@@ -193,6 +193,8 @@ int vsr_replay_candidates(const VsrModel* m, const uint32_t* cands, int n, void*
 typedef struct VsrSimOpts {
     int32_t device, depth;
     uint64_t num_walks, seed;
+    uint64_t probe_walks;   /* optional cross-check: for walks 0 .. probe_walks-1 the device reports ... */
+    uint64_t* probe_out;    /* ... [2w] = bytewise FP64 of the walk's last state (all words), [2w+1] = transitions taken; NULL = off */
 } VsrSimOpts;
 typedef struct VsrSimStats {
     uint64_t walks, steps, dead_ends, violating_walk;
@@ -201,6 +203,10 @@ typedef struct VsrSimStats {
 } VsrSimStats;
 int vsr_simulate(const VsrModel* m, const VsrSimOpts* opts, VsrSimStats* out, void* trace_out, uint8_t* trace_actions,
                  size_t trace_cap);
+
+/* the same walk on the host (walk index `walk` of vsr_simulate with this seed): chosen candidate indices, number of
+ * transitions, and the depth of the first violating state (0 = none) */
+int vsr_walk(const VsrModel* m, uint64_t seed, uint64_t walk, int depth, uint32_t* cands_out, int* violated_at);
 
 /* seen-set micro-benchmark: inserts n splitmix64 keys (a fraction dup_frac of them repeats) into a fresh
  * table of `capacity` slots (power of two) with the BFS's own insert routine; best of `iters` launches.

@@ -114,7 +114,8 @@ class VsrStats(C.Structure):
 
 
 class VsrSimOpts(C.Structure):
-    _fields_ = [("device", C.c_int32), ("depth", C.c_int32), ("num_walks", C.c_uint64), ("seed", C.c_uint64)]
+    _fields_ = [("device", C.c_int32), ("depth", C.c_int32), ("num_walks", C.c_uint64), ("seed", C.c_uint64),
+                ("probe_walks", C.c_uint64), ("probe_out", C.POINTER(C.c_uint64))]
 
 
 class VsrSimStats(C.Structure):
@@ -139,7 +140,7 @@ EXPORTED_SYMBOLS = [
     "vsr_engine_record_bytes", "vsr_engine_set_send_buffers", "vsr_engine_seed_init", "vsr_engine_expand", "vsr_engine_expand_part",
     "vsr_engine_insert_records", "vsr_engine_finish_level", "vsr_engine_frontier_size", "vsr_engine_read_frontier",
     "vsr_engine_trace_record", "vsr_engine_stats", "vsr_engine_reset", "vsr_engine_lookup", "vsr_engine_last_error", "vsr_engine_collected", "vsr_engine_build_trace",
-    "vsr_replay_candidates", "vsr_probe_bench", "vsr_simulate", "vsr_version",
+    "vsr_replay_candidates", "vsr_probe_bench", "vsr_simulate", "vsr_walk", "vsr_version",
 ]
 
 _lib = None
@@ -203,6 +204,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.vsr_engine_build_trace.argtypes = [vp, u64, vp, C.POINTER(C.c_uint8), C.c_size_t]
     lib.vsr_replay_candidates.argtypes = [vp, C.POINTER(C.c_uint32), C.c_int, vp, C.POINTER(C.c_uint8), C.c_size_t]
     lib.vsr_simulate.argtypes = [vp, C.POINTER(VsrSimOpts), C.POINTER(VsrSimStats), vp, C.POINTER(C.c_uint8), C.c_size_t]
+    lib.vsr_walk.argtypes = [vp, u64, u64, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_int)]
     lib.vsr_probe_bench.argtypes = [C.c_int, u64, u64, C.c_double, C.c_int, C.POINTER(C.c_double)]
     if path is None:
         _lib = lib
@@ -453,11 +455,15 @@ class ModelChecker:
         trace = [(ACTION_NAMES[acts[i]], raw[i * sb:(i + 1) * sb]) for i in range(int(st.trace_len))]
         return self.result_from_stats(st, rc, trace)
 
-    def simulate(self, num_walks: int = 1 << 20, depth: int = 100, seed: int = 1, device: int = 0):
+    def simulate(self, num_walks: int = 1 << 20, depth: int = 100, seed: int = 1, device: int = 0, probe_walks: int = 0):
         """TLC's `-simulate -depth N`: random behaviours on the GPU.  Returns (VsrSimStats, trace) — the trace is the
         violating behaviour [(action name, packed state)] when rc == 12, else []."""
         o = VsrSimOpts(device=device, depth=depth, num_walks=num_walks, seed=seed)
+        probe = (C.c_uint64 * max(2 * probe_walks, 1))()
+        if probe_walks:
+            o.probe_walks, o.probe_out = probe_walks, probe
         st = VsrSimStats()
+        self.last_probe = [(int(probe[2 * i]), int(probe[2 * i + 1])) for i in range(0)]
         cap = max(depth + 1, 2)
         tr = self._buf(cap)
         acts = (C.c_uint8 * cap)()
@@ -465,7 +471,15 @@ class ModelChecker:
         if rc == 153:
             raise VsrError(rc, "no usable CUDA device: simulation runs on the GPU only")
         raw, sb = bytes(tr), self.state_bytes
+        self.last_probe = [(int(probe[2 * i]), int(probe[2 * i + 1])) for i in range(probe_walks)]  # (fp of last state, transitions)
         return st, [(ACTION_NAMES[acts[i]], raw[i * sb:(i + 1) * sb]) for i in range(int(st.trace_len))]
+
+    def walk(self, seed: int, walk: int, depth: int):
+        """the same random walk on the host: (candidate indices, depth of the first violating state or 0)"""
+        cands = (C.c_uint32 * max(depth, 1))()
+        va = C.c_int()
+        n = self._lib.vsr_walk(self._h, seed, walk, depth, cands, C.byref(va))
+        return [int(cands[i]) for i in range(n)], int(va.value)
 
     def _check_stepwise(self, **kw) -> CheckResult:
         """Same BFS pumped level by level through the engine entry points (keeps every level for tests)."""

@@ -25,7 +25,7 @@ struct RunCfg {
     int symmetry;  /* SYMMETRY symmValues (VSR.cfg:31, VSR.tla:151) */
     int use_view;  /* VIEW view (VSR.cfg:29, VSR.tla:149-150) */
     int invariant; /* bitmask of INVARIANT names: 1 AcknowledgedWriteNotLost, 2 AcknowledgedWritesExistOnMajority,
-                      4 NoLogDivergence, 8 TestInv (VSR.tla:926-952) */
+                      4 NoLogDivergence, 8 TestInv (VSR.tla:926-952); 256 = test hook (see Ops::invariant) */
 };
 
 template <class L> struct Ops {
@@ -496,6 +496,11 @@ template <class L> struct Ops {
 
     /* invariants, VSR.tla:926-952; returns 0 if all selected hold, else the mask bit of the violated one */
     template <class W> static VSR_HD int invariant(const RunCfg& run, const W& w) {
+        if (run.invariant & 256) { /* test hook, not a spec invariant (only reachable through vsr_model_create): "no replica has
+                                      committed every value" — violated often, so tests can exercise the violation paths */
+            for (int r = 0; r < R; r++)
+                if ((int)VGET(L, COMMIT, w, r) == V) return 256;
+        }
         if (!(run.invariant & 3)) return 0; /* NoLogDivergence is vacuous (r1/r1, :931), TestInv is TRUE */
         for (int x = 0; x < V; x++) {
             if (VGET(L, ACKED, w, x) != ACK_TRUE) continue;

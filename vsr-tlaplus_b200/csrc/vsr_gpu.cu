@@ -619,6 +619,16 @@ int vsr_simulate(const VsrModel* m, const VsrSimOpts* o, VsrSimStats* out, void*
     q.first_bad = d;
     q.steps = d + 1;
     q.dead_ends = d + 2;
+    unsigned long long* dprobe = nullptr;
+    uint64_t* dtab = nullptr;
+    q.probe_walks = (o->probe_out && o->probe_walks) ? o->probe_walks : 0;
+    if (q.probe_walks > o->num_walks) q.probe_walks = o->num_walks;
+    if (q.probe_walks) {
+        if (cudaMalloc(&dprobe, q.probe_walks * 16) != cudaSuccess || cudaMalloc(&dtab, 8 * 256 * 8) != cudaSuccess) { cudaFree(d); return VSR_RC_SYSTEM; }
+        cudaMemcpy(dtab, fp64_table(), 8 * 256 * 8, cudaMemcpyHostToDevice);
+    }
+    q.probe_out = dprobe;
+    q.fp_tab = dtab;
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, o->device);
     cudaEvent_t a, b;
@@ -632,6 +642,9 @@ int vsr_simulate(const VsrModel* m, const VsrSimOpts* o, VsrSimStats* out, void*
     cudaEventElapsedTime(&ms, a, b);
     unsigned long long h[3];
     cudaMemcpy(h, d, 24, cudaMemcpyDeviceToHost);
+    if (q.probe_walks) cudaMemcpy(o->probe_out, dprobe, q.probe_walks * 16, cudaMemcpyDeviceToHost);
+    cudaFree(dprobe);
+    cudaFree(dtab);
     cudaFree(d);
     cudaEventDestroy(a);
     cudaEventDestroy(b);

@@ -659,6 +659,9 @@ struct SimParams {
     unsigned long long* first_bad; /* walk << 16 | depth of the state that violates (~0 = none) */
     unsigned long long* steps;     /* transitions taken */
     unsigned long long* dead_ends; /* walks that stopped in a state without successors */
+    unsigned long long* probe_out; /* optional: for walks 0 .. probe_walks-1, fingerprint of the last state and transitions taken */
+    unsigned long long probe_walks;
+    const uint64_t* fp_tab;
 };
 template <class L> __global__ void simulate_kernel(const SimParams Q) {
     unsigned long long steps = 0, dead = 0;
@@ -666,16 +669,22 @@ template <class L> __global__ void simulate_kernel(const SimParams Q) {
         uint64_t rng = Q.seed ^ (wk * 0xD1B54A32D192ED03ULL);
         uint32_t a[L::NW], b[L::NW];
         Ops<L>::init((uint32_t*)a);
+        unsigned long long mysteps = 0;
         for (int d = 2; d <= Q.depth; d++) {
             const int cand = Ops<L>::random_enabled(Q.run, (const uint32_t*)a, rng);
             if (cand < 0) { dead++; break; }
             if (Ops<L>::template step<true>(Q.run, (const uint32_t*)a, cand, (uint32_t*)b) <= 0) break;
             for (int j = 0; j < L::NW; j++) a[j] = b[j];
             steps++;
+            mysteps++;
             if (Ops<L>::invariant(Q.run, (const uint32_t*)a)) {
                 atomicMin(Q.first_bad, (wk << 16) | (unsigned long long)d);
                 break;
             }
+        }
+        if (wk < Q.probe_walks) {
+            Q.probe_out[2 * wk] = fp64_view<L>(Q.fp_tab, (const uint32_t*)a, false);
+            Q.probe_out[2 * wk + 1] = mysteps;
         }
     }
     for (int o = 16; o; o >>= 1) {

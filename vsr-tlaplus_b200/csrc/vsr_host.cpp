@@ -733,6 +733,30 @@ int vsr_action_location(const VsrModel* m, int a, char* buf, size_t cap) {
     return copy_out(m->action_location[a], buf, cap);
 }
 
+/* one random walk of simulation mode on the host: the walk `walk` of vsr_simulate(seed) exactly (same generator, same
+   step function).  cands_out receives the chosen candidate indices; returns the number of transitions taken;
+   *violated_at = depth (Init = 1) of the first state violating the invariant, 0 if none. */
+int vsr_walk(const VsrModel* m, uint64_t seed, uint64_t walk, int depth, uint32_t* cands_out, int* violated_at) {
+    const ModelOps* ops = m->ops;
+    uint32_t cur[VSR_MAX_STATE_BYTES / 4], nxt[VSR_MAX_STATE_BYTES / 4];
+    ops->init(cur);
+    uint64_t rng = seed ^ (walk * 0xD1B54A32D192ED03ULL);
+    int n = 0;
+    if (violated_at) *violated_at = 0;
+    for (int d = 2; d <= depth; d++) {
+        const int c = ops->random_enabled(&m->run, cur, &rng);
+        if (c < 0 || ops->step(&m->run, cur, c, nxt) <= 0) break;
+        memcpy(cur, nxt, ops->bytes);
+        if (cands_out) cands_out[n] = (uint32_t)c;
+        n++;
+        if (ops->invariant(&m->run, cur)) {
+            if (violated_at) *violated_at = d;
+            break;
+        }
+    }
+    return n;
+}
+
 int vsr_replay_candidates(const VsrModel* m, const uint32_t* cands, int n, void* trace_out, uint8_t* trace_actions, size_t trace_cap) {
     /* The engine explores canonical representatives; like TLC, the reported trace is re-executed from
        Init so that consecutive states are literal steps of Next with fixed value names. */
