@@ -421,8 +421,13 @@ int vsr_engine_finish_level(VsrEngine* e, VsrLevelInfo* out) {
     li.ms = e->level_ms_acc;
     if (c.overflow) {
         snprintf(e->last_error, sizeof e->last_error, "capacity exceeded (%s): %llu new states this level, frontier capacity %llu",
-                 c.overflow == 1 ? "frontier" : (c.overflow == 2 ? "tie list" : "send buffer"), (unsigned long long)c.out_count,
+                 c.overflow == 1 ? "frontier" : (c.overflow == 2 ? "tie list" : (c.overflow == 3 ? "send buffer" : "seen-set")), (unsigned long long)c.out_count,
                  (unsigned long long)e->frontier_cap);
+    }
+    if (!li.overflow && e->st.distinct + c.out_count > e->table_cap - e->table_cap / 8) {
+        li.overflow = 4; /* seen-set load above 7/8: probe chains explode long before it is literally full */
+        snprintf(e->last_error, sizeof e->last_error, "capacity exceeded (seen-set): %llu distinct states in %llu slots",
+                 (unsigned long long)(e->st.distinct + c.out_count), (unsigned long long)e->table_cap);
     }
     /* advance */
     const uint64_t n_new = c.out_count <= e->frontier_cap ? c.out_count : e->frontier_cap;

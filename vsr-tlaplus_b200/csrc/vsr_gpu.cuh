@@ -129,7 +129,7 @@ template <class L, class W> VSR_HD uint32_t check_hash(const W& w, bool use_view
     return h;
 }
 
-enum { INS_NEW = 0, INS_DUP = 1, INS_TIE = 2 };
+enum { INS_NEW = 0, INS_DUP = 1, INS_TIE = 2, INS_FULL = 3 };
 
 /* global state id = rank << 40 | local id; trace record = global id of the parent << 12 | candidate index
    (bit 63 is a transient "violates the invariant" mark inside the staging area) */
@@ -145,7 +145,8 @@ __device__ __forceinline__ uint64_t make_meta(int level, uint32_t auxkey, uint32
 __device__ __forceinline__ unsigned long long table_home(unsigned long long mask, uint64_t fp) { return mix64(fp) & mask; }
 __device__ __forceinline__ int table_insert_from(uint64_t* table, unsigned long long mask, unsigned long long h, uint64_t e0, uint64_t e1,
                                                  uint64_t fp, uint64_t meta, unsigned& probes, unsigned& collisions) {
-    for (;;) {
+    for (unsigned tries = 0;; tries++) {
+        if (tries > (1u << 16)) return INS_FULL; /* the table is (nearly) full: never spin forever, the host aborts with 152 */
         probes++;
         if (e0 == 0) {
             cas128(table + 2 * h, fp, meta, e0, e1);
@@ -314,6 +315,7 @@ template <class L> struct Expander {
                     gen += (unsigned long long)mult; /* successors sent to a peer are counted where they are inserted */
                     const int r = table_insert_from(P.table, P.table_mask, home, first.x, first.y, fp, meta, probes, coll);
                     isnew = r == INS_NEW;
+                    if (r == INS_FULL) atomicExch(&P.ctr->overflow, 4);
                     if (isnew) bad = O_::invariant(P.run, n);
                     if (r == INS_TIE) {
                         ties++;
@@ -551,6 +553,7 @@ template <class L> __global__ void __launch_bounds__(256) insert_kernel(const In
         const uint64_t meta = h->meta ? h->meta : make_meta(P.level, Ops<L>::aux_key(n), check_hash<L>(n, P.run.use_view != 0));
         const int r = table_insert(P.table, P.table_mask, h->fp, meta, probes, coll);
         isnew = r == INS_NEW;
+        if (r == INS_FULL) atomicExch(&P.ctr->overflow, 4);
         gen = h->mult;
         if (r == INS_TIE) {
             nties = 1;
