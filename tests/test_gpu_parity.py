@@ -249,3 +249,41 @@ def test_simulation_mode_walks_like_the_host_and_replays_violations(pkg):
     st2, trace2 = hook.simulate(num_walks=1 << 16, depth=40, seed=5)
     assert (st2.violating_walk, st2.violation_depth, st2.steps) == (st.violating_walk, st.violation_depth, st.steps)
     assert [s for _, s in trace2] == [s for _, s in trace]
+
+
+def test_shipped_cfg_full_size_properties(pkg):
+    """BASELINE configs[1] at FULL size (the shipped VSR.cfg constants, 1.17e9 states: far beyond what the oracle can enumerate),
+    through size-independent properties:
+      * two complete explorations with different seen-set capacities (different probe sequences, different arrival orders)
+        give identical per-depth counts, totals and depth: the result does not depend on scheduling;
+      * distinct = sum of level sizes; generated = 1 + sum of per-level generated; the last level generates successors but no
+        new state; no VIEW ties and no fingerprint collisions were detected;
+      * the first violating depth is the same in both, and the counterexample of one run replays through the ORACLE's Next
+        step by step with only its last state violating AcknowledgedWriteNotLost (checked up to value relabelling);
+      * the bounded-depth prefix agrees with the oracle-verified level sizes of test_bounded_depth_matches_oracle."""
+    mc = pkg.ModelChecker.from_cfg_text(pkg.cfg_text(3, ["v1", "v2"], 2))
+    a = mc.check(stop_on_violation=False, table_capacity=1 << 31, frontier_capacity=130_000_000)
+    b = mc.check(stop_on_violation=False, table_capacity=1 << 32, frontier_capacity=125_000_000, keep_trace=False)
+    for r in (a, b):
+        assert r.complete and r.error_code == 0 and r.queue == 0
+        assert r.distinct == sum(r.level_sizes) == 1173992337
+        assert r.generated == 1 + sum(r.level_generated) == 3129587684
+        assert r.depth == len(r.level_sizes) == 47 and r.level_generated[-1] == 0
+        assert r.h2_ties == 0 and r.fp_collisions == 0
+        assert r.violation_level == 28
+    assert a.level_sizes == b.level_sizes and a.level_generated == b.level_generated
+    assert a.level_sizes[:11] == [1, 3, 10, 35, 124, 403, 1200, 3319, 8500, 20030, 43306]
+    # the counterexample (run a kept parent records): literal behaviour, oracle-validated
+    assert a.rc == 12 and len(a.trace) == 28
+    q = orc.params(3, 2, 2, symmetry=False)
+    L = orc.lib()
+    flats = [mc.unpack(s) for _, s in a.trace]
+    for i in range(27):
+        cap = 256
+        succ = (pkg.checker.VsrFlatState * cap)()
+        acts = (C.c_int * cap)()
+        n = L.orc_successors_flat(q, C.byref(flats[i]), succ, acts, cap)
+        want = orc.digests_full_of(q, (pkg.checker.VsrFlatState * 1)(flats[i + 1]))[0]
+        got = orc.digests_full_of(q, succ)[:n]
+        assert any(g == want and pkg.ACTION_NAMES[acts[k]] == a.trace[i + 1][0] for k, g in enumerate(got)), f"step {i + 1}"
+    assert [L.orc_invariant_flat(q, C.byref(f)) for f in flats] == [1] * 27 + [0]
