@@ -6,19 +6,22 @@
  *   E1  successor enumeration   Ops<L>::step over the candidate (action, binding) index space
  *   E2  SYMMETRY                kept incrementally by step (canonical value labels)
  *   E3  VIEW                    mask of the aux bits inside fp64_view
- *   E4  fingerprint             FP64 (Rabin) of the packed VIEW bytes + a 32-bit check hash
+ *   E4  fingerprint             FP64 (Rabin, slicing-by-8 tables in shared memory) of the packed VIEW bytes + a 32-bit check hash
  *   E5  seen-set                open-addressed HBM table of 16-byte {fp, meta} entries, one 128-bit load per
- *                               probe, insertion by one 128-bit CAS (ATOMG.E.CAS.128)
+ *                               probe (issued as soon as the fingerprint is known), insertion by one 128-bit CAS
+ *                               (ATOMG.E.CAS.128); probing is bounded, a full table is an error, never a spin
  *   E6  queue                   next frontier staged per warp in shared memory, flushed 32 states at a time
  *                               by a TMA bulk store (cp.async.bulk.global.shared::cta, UBLKCP)
  *   E7  invariant               evaluated inline on every newly inserted state
  *   E8  trace                   (parent id, candidate) per new state
  *   E9  deadlock                states with no enabled candidate
- * Work shape: a warp takes 32 frontier states; every lane evaluates the GUARD of each
- * candidate on its own state (uniform control flow: the candidate index is warp-uniform), enabled
- * (lane, candidate) pairs are compacted into a warp queue, and whenever 32 are queued the whole warp
- * applies them — one successor per lane — so the expensive part (apply, fingerprint, probe) runs
- * with full lanes whatever the enabled-candidate density.
+ * Work shape: a block takes 32*WARPS frontier states, one per thread.  SCAN: all warps walk Next's 13
+ * action groups together (a barrier per group); every thread evaluates that group's guards on its own state (the
+ * candidate index is warp-uniform, so is the control flow) and enabled (state, candidate) pairs are ballot-compacted
+ * into a block pool, which ends up grouped by action.  APPLY: warps take batches of 32 pairs of ONE action and apply
+ * them one per lane — the successor is built in a rotated shared-memory row, fingerprinted, probed, inserted — so the
+ * expensive part runs with full lanes, without divergence between actions, and with one action's code live at a time.
+ * See profiles/round1_expand_kernel.md for the measurements that led here.
  */
 #ifndef VSR_GPU_CUH
 #define VSR_GPU_CUH
