@@ -30,16 +30,18 @@ def test_packed_next_equals_oracle_on_complete_spaces(R, V, L, sym, n):
     assert out["complete"] == 1 and out["mismatches"] == 0 and out["assumption_violations"] == 0
 
 
-@pytest.mark.parametrize("R,V,L,sym", [(3, 2, 2, 1), (3, 3, 3, 1), (5, 2, 2, 1), (3, 3, 3, 0), (4, 2, 2, 1), (3, 3, 2, 1)])
+@pytest.mark.parametrize("R,V,L,sym", [(3, 2, 2, 1), (3, 3, 3, 1), (5, 2, 2, 1), (3, 3, 3, 0), (4, 2, 2, 1), (3, 3, 2, 1), (5, 3, 2, 1),
+                                        (4, 3, 2, 1), (3, 2, 3, 1), (2, 3, 2, 0), (5, 1, 1, 0)])
 def test_packed_next_equals_oracle_bfs_prefix(R, V, L, sym):
-    out = run_diff(R, V, L, sym, 12000)
-    assert out["checked"] == 12000 and out["mismatches"] == 0
+    out = run_diff(R, V, L, sym, 8000)
+    assert out["checked"] == 8000 and out["mismatches"] == 0
 
 
-@pytest.mark.parametrize("R,V,L,sym,seed", [(3, 2, 2, 1, 1), (3, 3, 3, 1, 2), (5, 2, 2, 1, 3), (3, 3, 3, 0, 4), (3, 2, 2, 0, 5)])
+@pytest.mark.parametrize("R,V,L,sym,seed", [(3, 2, 2, 1, 1), (3, 3, 3, 1, 2), (5, 2, 2, 1, 3), (3, 3, 3, 0, 4), (3, 2, 2, 0, 5), (5, 3, 2, 1, 6),
+                                             (4, 3, 2, 1, 7)])
 def test_packed_next_equals_oracle_on_random_walks(R, V, L, sym, seed):
     """simulation-style deep coverage: state transfer, view-change completion and log truncation only happen 15+ steps in"""
-    out = run_diff(R, V, L, sym, 12000, 1, 100000, seed)
+    out = run_diff(R, V, L, sym, 8000, 1, 100000, seed)
     assert out["mismatches"] == 0 and out["max_walk_depth"] >= 30
 
 

@@ -13,7 +13,8 @@
 /* (ReplicaCount, |Values|, 1 + StartViewOnTimerLimit) combinations compiled in.  BASELINE.json
    configs: (2,1,2) cfg1, (3,2,3) cfg2 = shipped VSR.cfg, (3,3,4) cfg3 = README, (5,2,3) cfg4. */
 #define VSR_FOR_EACH_CONFIG(X) \
-    X(2, 1, 2) X(2, 2, 3) X(3, 1, 2) X(3, 1, 3) X(3, 2, 2) X(3, 2, 3) X(3, 3, 3) X(3, 3, 4) X(4, 2, 3) X(5, 2, 3)
+    X(2, 1, 2) X(2, 2, 2) X(2, 2, 3) X(2, 3, 3) X(3, 1, 2) X(3, 1, 3) X(3, 2, 2) X(3, 2, 3) X(3, 2, 4) X(3, 3, 2) X(3, 3, 3) \
+    X(3, 3, 4) X(4, 1, 2) X(4, 2, 2) X(4, 2, 3) X(4, 3, 3) X(5, 1, 2) X(5, 2, 2) X(5, 2, 3) X(5, 3, 3)
 
 namespace vsr {
 
