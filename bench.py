@@ -237,26 +237,30 @@ def main():
                      "how": "vsr_probe_bench: %d splitmix64 keys (50%% repeats) into a fresh table of %d slots with the BFS's own "
                             "insert routine, best of 3: %.3f ms; achieved = this rank's seen-set probes per kernel-second of the BFS"
                             % (nkeys, table_cap, eng_probe_out[0])}
-    barrier()
-    te = time.time()
-    if world == 1:
-        r2 = pkg.ModelChecker.from_cfg_text(cfg).check(stop_on_violation=False, table_capacity=table_cap, frontier_capacity=frontier_cap)
-        e2e_states, h2d, d2h = r2.distinct, r2.bytes_h2d + len(cfg), r2.bytes_d2h + C.sizeof(pkg.checker.VsrStats)
-        ok = ok and r2.distinct == EXPECT["distinct"] and r2.rc == 12 and len(r2.trace) == EXPECT["violation_level"]
-    else:
-        mc2 = pkg.ModelChecker.from_cfg_text(cfg)
-        eng2 = vdist.GpuEngine(mc2, rank, world, device=local, table_capacity=table_cap, frontier_capacity=frontier_cap,
-                               send_capacity=send_cap, keep_trace=True)
-        r2 = vdist.ShardedBfs(eng2, rank, world).run(stop_on_violation=False, want_trace=True)
-        st2 = eng2.stats()
-        e2e_states, h2d, d2h = r2.distinct, int(st2.bytes_h2d) + len(cfg), int(st2.bytes_d2h)
-        eng2.close()
-    barrier()
-    e2e_s = time.time() - te
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
-    e2e_s = float(t[0])
+    # e2e is dominated by allocating and clearing tens of GB (cudaMalloc of a 32 GiB seen-set takes 0.05-1.5 s depending on the
+    # box's allocator state), so it is run three times and the median is reported, with all three in the JSON
+    e2e_runs = []
+    for _ in range(3):
+        barrier()
+        te = time.time()
+        if world == 1:
+            r2 = pkg.ModelChecker.from_cfg_text(cfg).check(stop_on_violation=False, table_capacity=table_cap, frontier_capacity=frontier_cap)
+            e2e_states, h2d, d2h = r2.distinct, r2.bytes_h2d + len(cfg), r2.bytes_d2h + C.sizeof(pkg.checker.VsrStats)
+            ok = ok and r2.distinct == EXPECT["distinct"] and r2.rc == 12 and len(r2.trace) == EXPECT["violation_level"]
+        else:
+            mc2 = pkg.ModelChecker.from_cfg_text(cfg)
+            eng2 = vdist.GpuEngine(mc2, rank, world, device=local, table_capacity=table_cap, frontier_capacity=frontier_cap,
+                                   send_capacity=send_cap, keep_trace=True)
+            r2 = vdist.ShardedBfs(eng2, rank, world).run(stop_on_violation=False, want_trace=True)
+            st2 = eng2.stats()
+            e2e_states, h2d, d2h = r2.distinct, int(st2.bytes_h2d) + len(cfg), int(st2.bytes_d2h)
+            eng2.close()
+        barrier()
+        t = torch.tensor([time.time() - te], dtype=torch.float64, device=dev)
+        if world > 1:
+            tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        e2e_runs.append(float(t[0]))
+    e2e_s = sorted(e2e_runs)[1]
 
     if rank == 0:
         out = {
@@ -280,7 +284,7 @@ def main():
                          "peak_source": peak_src, "bytes_per_state": b_alg, "g": g,
                          "kernel": "expand_kernel<Layout<3,2,3>> (per-GPU states x B_alg / sum of per-level kernel time, max over ranks)"},
             "e2e": {"value": e2e_states / e2e_s, "unit": "states/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "seconds": e2e_s, "api": "ModelChecker.from_cfg_text(cfg).check()" if world == 1 else "dist.GpuEngine + dist.ShardedBfs.run()"},
+                    "seconds": e2e_s, "seconds_all_runs": e2e_runs, "api": "ModelChecker.from_cfg_text(cfg).check()" if world == 1 else "dist.GpuEngine + dist.ShardedBfs.run()"},
             "probe_roofline": probe,
             "clocks": clocks,
         }

@@ -200,6 +200,14 @@ int vsr_engine_create(const VsrModel* m, const VsrRunOpts* opts, int rank, int w
     if ((ce = cudaGetDeviceProperties(&prop, e->device)) != cudaSuccess) return bail("cudaGetDeviceProperties", ce);
     e->sms = prop.multiProcessorCount;
     if ((ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", ce);
+    { /* keep freed device memory in the driver's pool: a process that checks one model after another (bench e2e, a service)
+         does not pay the page-mapping cost of tens of GB again */
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, e->device) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     cudaEventCreate(&e->ev0);
     cudaEventCreate(&e->ev1);
     if ((ce = e->g->prepare(&e->blocks_per_sm)) != cudaSuccess) return bail("kernel attributes", ce);
@@ -220,20 +228,20 @@ int vsr_engine_create(const VsrModel* m, const VsrRunOpts* opts, int rank, int w
     e->frontier_cap = fcap;
     e->trace_cap = opts->keep_trace ? tcap / 2 + 64 : 0;
     e->tie_cap = 1 << 16;
-    if ((ce = cudaMalloc(&e->table, tcap * 16)) != cudaSuccess) return bail("cudaMalloc(seen-set)", ce);
+    if ((ce = cudaMallocAsync((void**)&e->table, tcap * 16, e->stream)) != cudaSuccess) return bail("cudaMalloc(seen-set)", ce);
     if ((ce = cudaMemsetAsync(e->table, 0, tcap * 16, e->stream)) != cudaSuccess) return bail("memset", ce);
     for (int i = 0; i < 2; i++)
-        if ((ce = cudaMalloc(&e->frontier[i], fcap * S)) != cudaSuccess) return bail("cudaMalloc(frontier)", ce);
-    if (e->trace_cap && (ce = cudaMalloc(&e->trace, e->trace_cap * 8)) != cudaSuccess) return bail("cudaMalloc(trace)", ce);
-    if ((ce = cudaMalloc(&e->ctr, sizeof(DevCounters))) != cudaSuccess) return bail("cudaMalloc", ce);
-    if ((ce = cudaMalloc(&e->ties, e->tie_cap * (size_t)e->g->tie_bytes)) != cudaSuccess) return bail("cudaMalloc", ce);
-    if ((ce = cudaMalloc(&e->fp_tab, 8 * 256 * 8)) != cudaSuccess) return bail("cudaMalloc", ce);
+        if ((ce = cudaMallocAsync((void**)&e->frontier[i], fcap * S, e->stream)) != cudaSuccess) return bail("cudaMalloc(frontier)", ce);
+    if (e->trace_cap && (ce = cudaMallocAsync((void**)&e->trace, e->trace_cap * 8, e->stream)) != cudaSuccess) return bail("cudaMalloc(trace)", ce);
+    if ((ce = cudaMallocAsync((void**)&e->ctr, sizeof(DevCounters), e->stream)) != cudaSuccess) return bail("cudaMalloc", ce);
+    if ((ce = cudaMallocAsync((void**)&e->ties, e->tie_cap * (size_t)e->g->tie_bytes, e->stream)) != cudaSuccess) return bail("cudaMalloc", ce);
+    if ((ce = cudaMallocAsync((void**)&e->fp_tab, 8 * 256 * 8, e->stream)) != cudaSuccess) return bail("cudaMalloc", ce);
     if (world > 1) { /* sender-side duplicate filter: 1/8 of the seen-set's slots, 8 B each */
         e->sent_cap = tcap / 8 < (1ull << 16) ? (1ull << 16) : tcap / 8;
-        if ((ce = cudaMalloc(&e->sent_cache, e->sent_cap * 8)) != cudaSuccess) return bail("cudaMalloc(sent filter)", ce);
+        if ((ce = cudaMallocAsync((void**)&e->sent_cache, e->sent_cap * 8, e->stream)) != cudaSuccess) return bail("cudaMalloc(sent filter)", ce);
         if ((ce = cudaMemsetAsync(e->sent_cache, 0, e->sent_cap * 8, e->stream)) != cudaSuccess) return bail("memset", ce);
     }
-    if ((ce = cudaMalloc(&e->init_rec, e->g->rec_bytes)) != cudaSuccess) return bail("cudaMalloc", ce);
+    if ((ce = cudaMallocAsync((void**)&e->init_rec, e->g->rec_bytes, e->stream)) != cudaSuccess) return bail("cudaMalloc", ce);
     if ((ce = cudaMemcpyAsync(e->fp_tab, fp64_table(), 8 * 256 * 8, cudaMemcpyHostToDevice, e->stream)) != cudaSuccess) return bail("memcpy", ce);
     e->st.table_capacity = tcap;
     e->st.frontier_capacity = fcap;
@@ -247,18 +255,18 @@ int vsr_engine_create(const VsrModel* m, const VsrRunOpts* opts, int rank, int w
 
 void vsr_engine_destroy(VsrEngine* e) {
     if (!e) return;
-    cudaFree(e->table);
-    cudaFree(e->frontier[0]);
-    cudaFree(e->frontier[1]);
-    cudaFree(e->trace);
-    cudaFree(e->ctr);
-    cudaFree(e->ties);
-    cudaFree(e->fp_tab);
-    cudaFree(e->init_rec);
-    cudaFree(e->sent_cache);
+    if (e->stream) cudaFreeAsync(e->table, e->stream); else cudaFree(e->table);
+    if (e->stream) cudaFreeAsync(e->frontier[0], e->stream); else cudaFree(e->frontier[0]);
+    if (e->stream) cudaFreeAsync(e->frontier[1], e->stream); else cudaFree(e->frontier[1]);
+    if (e->stream) cudaFreeAsync(e->trace, e->stream); else cudaFree(e->trace);
+    if (e->stream) cudaFreeAsync(e->ctr, e->stream); else cudaFree(e->ctr);
+    if (e->stream) cudaFreeAsync(e->ties, e->stream); else cudaFree(e->ties);
+    if (e->stream) cudaFreeAsync(e->fp_tab, e->stream); else cudaFree(e->fp_tab);
+    if (e->stream) cudaFreeAsync(e->init_rec, e->stream); else cudaFree(e->init_rec);
+    if (e->stream) cudaFreeAsync(e->sent_cache, e->stream); else cudaFree(e->sent_cache);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
-    if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->stream) { cudaStreamSynchronize(e->stream); cudaStreamDestroy(e->stream); }
     delete e;
 }
 
