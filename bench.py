@@ -103,8 +103,51 @@ def oracle_sample(seconds, workers):
     return dict(distinct=int(scal[1]), generated=int(scal[0]), depth=int(scal[3]), seconds=dt, rate=int(scal[1]) / dt)
 
 
+def try_tlc(seconds):
+    """if a JVM and tla2tools.jar ever appear on the box ($TLA2TOOLS_JAR) together with the spec ($VSR_TLA, or the
+    reference checkout), run the REAL reference — TLC — on the same config for a bounded time and return its rate.  In this
+    image there is no java, so this returns None and the CPU restatement stands in."""
+    import re
+    import shutil
+    import tempfile
+    jar, java = os.environ.get("TLA2TOOLS_JAR"), shutil.which("java")
+    tla = os.environ.get("VSR_TLA", "/root/reference/vsr-revisited/paper/VSR.tla")
+    if not (jar and java and os.path.exists(jar) and os.path.exists(tla)):
+        return None
+    import _pkg
+    pkg = _pkg.load()
+    d = tempfile.mkdtemp()
+    shutil.copy(tla, os.path.join(d, "VSR.tla"))
+    with open(os.path.join(d, "VSR.cfg"), "w") as f:
+        f.write(pkg.cfg_text(WORKLOAD["R"], ["v1", "v2"], WORKLOAD["L"]))
+    t0 = time.time()
+    try:
+        out = subprocess.run([java, "-cp", jar, "tlc2.TLC", "-workers", "auto", "-deadlock", "-continue", "-config", "VSR.cfg", "VSR.tla"],
+                             cwd=d, capture_output=True, text=True, timeout=seconds).stdout
+    except subprocess.TimeoutExpired as e:
+        out = (e.stdout or b"").decode() if isinstance(e.stdout, bytes) else (e.stdout or "")
+    dt = time.time() - t0
+    m = re.findall(r"([\d,]+) states generated.*?([\d,]+) distinct states found", out)
+    if not m:
+        return None
+    distinct = int(m[-1][1].replace(",", ""))
+    return dict(distinct=distinct, seconds=dt, rate=distinct / dt)
+
+
 def run_reference(args, rank):
     if rank != 0:
+        return
+    tlc = try_tlc(30.0)
+    if tlc:
+        cores = os.cpu_count() or 1
+        print(json.dumps({
+            "impl": "reference", "metric": "unique states explored/sec (VSR.tla, shipped VSR.cfg constants)", "value": tlc["rate"],
+            "unit": "states/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": 1e3 * tlc["seconds"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "none (state space of the config)",
+            "config": {"workload": "VSR.tla shipped VSR.cfg constants under TLC (-workers auto -deadlock -continue), bounded run"},
+            "cpu_baseline": {"value": tlc["rate"], "unit": "states/s", "cores": cores, "kind": "reference",
+                             "sample": "tlc2.TLC for %.0f s: %d distinct states" % (tlc["seconds"], tlc["distinct"])},
+            "e2e": {"value": tlc["rate"], "unit": "states/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
     cores = os.cpu_count() or 1
     per_step = 10.0
