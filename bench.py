@@ -29,7 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(R=3, V=2, L=2)           # BASELINE configs[1] = vsr-revisited/paper/VSR.cfg
-TABLE_CAP = 1 << 31                      # 2^31 slots * 16 B = 32 GiB (1.17e9 states -> load 0.55)
+TABLE_CAP = 1 << 31                      # 2^31 slots * 16 B = 32 GiB (1.17e9 states -> load 0.55) + 15 GiB of trace records
 FRONTIER_CAP = 140_000_000               # widest level: 120,193,500 states
 EXPECT = dict(distinct=1173992337, generated=3129587684, depth=47, violation_level=28)
 

@@ -217,16 +217,16 @@ int vsr_engine_create(const VsrModel* m, const VsrRunOpts* opts, int rank, int w
     cudaMemGetInfo(&free_b, &total_b);
     uint64_t tcap = opts->table_capacity, fcap = opts->frontier_capacity;
     const uint64_t S = (uint64_t)e->g->bytes;
-    if (!tcap) { /* table 16 B/slot + trace 8 B per state at load <= 1/2  ->  20 B per slot; give it ~45% of free memory */
+    if (!tcap) { /* table 16 B/slot + trace 8 B per state at load <= 7/8  ->  23 B per slot; give it ~45% of free memory */
         tcap = 1;
-        while (tcap * 2 * 20 <= (uint64_t)(free_b * 0.45)) tcap *= 2;
+        while (tcap * 2 * 23 <= (uint64_t)(free_b * 0.45)) tcap *= 2;
     }
     if (tcap & (tcap - 1)) { uint64_t p2 = 1; while (p2 < tcap) p2 *= 2; tcap = p2; }
     if (!fcap) fcap = (uint64_t)(free_b * 0.40) / (2 * S);
     if (fcap < 64) fcap = 64;
     e->table_cap = tcap;
     e->frontier_cap = fcap;
-    e->trace_cap = opts->keep_trace ? tcap / 2 + 64 : 0;
+    e->trace_cap = opts->keep_trace ? tcap - tcap / 8 + 64 : 0; /* one record per distinct state, up to the seen-set's load limit */
     e->tie_cap = 1 << 16;
     if ((ce = cudaMallocAsync((void**)&e->table, tcap * 16, e->stream)) != cudaSuccess) return bail("cudaMalloc(seen-set)", ce);
     if ((ce = cudaMemsetAsync(e->table, 0, tcap * 16, e->stream)) != cudaSuccess) return bail("memset", ce);

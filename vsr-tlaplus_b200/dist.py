@@ -245,6 +245,9 @@ class ShardedBfs:
                 break
             if max_depth and level >= max_depth:
                 break
+            if level >= 254:  # the seen-set tags entries with an 8-bit depth
+                result = 152
+                break
             if max_states and r.distinct >= max_states:
                 break
             if max_seconds:
