@@ -151,7 +151,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("VSR_B200_LIB") or LIB_PATH  # VSR_B200_LIB: tuning experiments with a variant build
     if not os.path.exists(p):
         raise VsrError(153, f"{p} not found: build it first (python -c 'import __graft_entry__ as g; g.build()'); "
                             "there is no Python/CPU fallback for the CUDA path")

@@ -216,7 +216,11 @@ template <class L, int WARPS> struct BlockSmemT {
 };
 /* warps per block: as many as fit twice per SM (2 x <= 113 KB of shared memory) */
 template <class L> struct ExpandCfg {
+#ifdef VSR_FORCE_WARPS
+    static constexpr int WARPS = VSR_FORCE_WARPS; /* tuning experiments only */
+#else
     static constexpr int WARPS = sizeof(BlockSmemT<L, 16>) <= 113 * 1024 ? 16 : (sizeof(BlockSmemT<L, 12>) <= 113 * 1024 ? 12 : 8);
+#endif
     typedef BlockSmemT<L, WARPS> Smem;
 };
 
