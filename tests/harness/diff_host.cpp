@@ -8,10 +8,12 @@
  *       ==  multiset of the product's successors (each counted `mult` times),
  *   - pack(unpack(s)) == s, invariant verdicts equal, aux tie-break keys equal,
  *   - the oracle's audit of the slot-encoding assumptions stays at zero.
- * usage: diff_host R V L sym(0/1) max_states [inv_mask [walks seed]]   (walks > 0: random walks instead of BFS)
+ * usage: diff_host R V L sym(0/1) max_states [inv_mask [walks seed [start_states.hex]]]   (walks > 0: random walks instead of
+ *        BFS, optionally started from given packed states — e.g. the golden trace's, to reach the state-transfer actions)
  * prints one JSON line; exit 0 iff no mismatch.
  */
 #include <algorithm>
+#include <cctype>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -30,6 +32,7 @@ int main(int argc, char** argv) {
     const int inv_mask = argc > 6 ? atoi(argv[6]) : 1;
     const int walks = argc > 7 ? atoi(argv[7]) : 0;
     const uint64_t seed = argc > 8 ? strtoull(argv[8], 0, 10) : 1;
+    const char* seeds_path = argc > 9 ? argv[9] : nullptr; /* optional: hex-encoded packed states to start the walks from */
     char err[512];
     VsrModel* m = nullptr;
     int rc = vsr_model_create(R, 1, V, Lm, 0, sym, 1, inv_mask, &m, err, sizeof err);
@@ -49,6 +52,7 @@ int main(int argc, char** argv) {
     seen.insert(s0);
     size_t checked = 0, mism = 0, succ_total = 0, depth = 1, pack_bad = 0, inv_bad = 0, aux_bad = 0, canon_bad = 0;
     uint64_t assump = 0;
+    uint64_t action_cover[VSR_NUM_ACTIONS] = {0}; /* successors compared, per action of Next */
     std::vector<char> succbuf((size_t)SB * 1024);
     std::vector<uint8_t> acts(1024);
     std::vector<uint32_t> mult(1024);
@@ -98,6 +102,7 @@ int main(int argc, char** argv) {
             uint64_t d[2];
             orc::digest128(key, d);
             got[{(int)acts[i], {d[0], d[1]}}] += (int)mult[i];
+            action_cover[acts[i] < VSR_NUM_ACTIONS ? acts[i] : 0] += mult[i];
             succ_total += mult[i];
             succs.emplace_back(t, SB);
         }
@@ -122,8 +127,23 @@ int main(int argc, char** argv) {
         /* random walks (simulation): reaches the deep states a bounded BFS cannot */
         uint64_t rng = seed * 0x9E3779B97F4A7C15ULL + 1;
         auto rnd = [&]() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return rng; };
+        std::vector<std::string> starts;
+        if (seeds_path) {
+            FILE* sf = fopen(seeds_path, "r");
+            char line[2048];
+            while (sf && fgets(line, sizeof line, sf)) {
+                std::string st;
+                for (size_t i = 0; i + 1 < strlen(line) && isxdigit((unsigned char)line[i]); i += 2) {
+                    unsigned v;
+                    sscanf(line + i, "%2x", &v);
+                    st.push_back((char)v);
+                }
+                if ((int)st.size() == SB) starts.push_back(st);
+            }
+            if (sf) fclose(sf);
+        }
         for (int wk = 0; wk < walks && !stop; wk++) {
-            std::string cur = s0;
+            std::string cur = starts.empty() ? s0 : starts[rnd() % starts.size()];
             for (size_t d = 1;; d++) {
                 if (checked >= max_states) { stop = true; break; }
                 depth = d;
@@ -147,10 +167,12 @@ int main(int argc, char** argv) {
         }
         if (!stop) { frontier.swap(next); depth++; }
     }
+    std::string cover;
+    for (int a = 1; a <= 15; a++) cover += (a > 1 ? ", " : "") + std::to_string(action_cover[a]);
     printf("{\"R\": %d, \"V\": %d, \"L\": %d, \"sym\": %d, \"state_bytes\": %d, \"checked\": %zu, \"distinct_full\": %zu, \"successors\": %zu, "
            "\"depth\": %zu, \"complete\": %d, \"mismatches\": %zu, \"pack_roundtrip_bad\": %zu, \"invariant_bad\": %zu, \"aux_key_bad\": %zu, "
-           "\"canon_bad\": %zu, \"assumption_violations\": %llu, \"walks\": %d, \"max_walk_depth\": %zu, \"violating_states_seen\": %zu, \"first_bad\": \"%s\"}\n",
+           "\"canon_bad\": %zu, \"assumption_violations\": %llu, \"walks\": %d, \"max_walk_depth\": %zu, \"violating_states_seen\": %zu, \"first_bad\": \"%s\", \"action_coverage\": [%s]}\n",
            R, V, Lm, sym, SB, checked, seen.size(), succ_total, depth, stop ? 0 : 1, mism, pack_bad, inv_bad, aux_bad, canon_bad,
-           (unsigned long long)assump, walks, max_walk_depth, violations_seen, first_bad.c_str());
+           (unsigned long long)assump, walks, max_walk_depth, violations_seen, first_bad.c_str(), cover.c_str());
     return (mism || pack_bad || inv_bad || aux_bad || canon_bad || assump) ? 1 : 0;
 }

@@ -200,3 +200,23 @@ def test_sliced_fingerprint_equals_bytewise_definition(pkg):
                 s = mc.init_state()
                 continue
             s = rnd.choice(succ)[0]
+
+
+@pytest.mark.parametrize("sym", [1, 0])
+def test_every_action_is_compared_with_the_oracle(pkg, tmp_path, sym):
+    """Uniform random walks from Init and shallow BFS prefixes never enable the state-transfer actions (SendGetState needs a
+    Prepare from a higher view with a gap: 16+ steps in), and the golden trace never takes ReceiveHigherDVC, ReceiveGetState or
+    ReceiveNewState.  Walks started from the 24 golden-trace states reach all of them: every one of the 15 actions
+    that can fire with RestartEmptyLimit = 0 must have successors compared with the oracle's, with no mismatch."""
+    import base64, zlib
+    fx = json.load(open(os.path.join(ROOT, "tests", "golden", "state_transfer_trace.json")))
+    Flat = pkg.checker.VsrFlatState
+    mc = pkg.ModelChecker.from_constants(3, 3, 3, symmetry=bool(sym))
+    seeds = tmp_path / "seeds.hex"
+    seeds.write_text("".join(mc.pack(Flat.from_buffer_copy(zlib.decompress(base64.b64decode(s["flat_zlib_b64"])))).hex() + "\n"
+                             for s in fx["states"]))
+    out = run_diff(3, 3, 3, sym, 40000, 1, 1000000, 5, str(seeds))
+    assert out["mismatches"] == 0 and out["checked"] == 40000
+    cover = dict(zip(pkg.ACTION_NAMES[1:16], out["action_coverage"]))
+    assert all(n > 0 for n in cover.values()), cover
+    assert cover["SendGetState"] >= 50 and cover["ReceiveGetState"] >= 100 and cover["ReceiveNewState"] >= 10, cover
