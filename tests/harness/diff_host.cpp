@@ -94,6 +94,11 @@ int main(int argc, char** argv) {
         }
         int n = vsr_successors(m, s.data(), succbuf.data(), 1024, acts.data(), mult.data());
         if (n < 0) { mism++; if (first_bad.empty()) first_bad = "vsr_successors error " + std::to_string(n); return; }
+        {   /* the register-mask form of the guards (the GPU scan's) against the one-candidate form: checked inside the call */
+            uint32_t en[1024];
+            const int ne = vsr_enabled_candidates(m, s.data(), en, 1024);
+            if (ne != n) { mism++; if (first_bad.empty()) first_bad = "vsr_enabled_candidates " + std::to_string(ne) + " vs successors " + std::to_string(n); return; }
+        }
         for (int i = 0; i < n; i++) {
             const char* t = succbuf.data() + (size_t)i * SB;
             if (vsr_unpack(m, t, g) != 0) { mism++; continue; }

@@ -17,6 +17,8 @@
 #ifndef VSR_ACTIONS_H
 #define VSR_ACTIONS_H
 
+#include <utility>
+
 #include "vsr_layout.h"
 
 namespace vsr {
@@ -35,10 +37,10 @@ template <class L> struct Ops {
     static VSR_HD int oidx(int a, int b) { return b < a ? b : b - 1; }   /* index of b among replicas \ {a} */
     static VSR_HD int oinv(int a, int i) { return i < a ? i : i + 1; }
 
-    template <int B, class W> static VSR_HD int loglen(const W& w, int row) {
+    template <int B, int N = 0, class W> static VSR_HD int loglen(const W& w, int row) { /* N: rows x V elements of the field */
         int n = 0;
         for (int i = 0; i < V; i++) {
-            if (fget<B, L::OB>(w, row * V + i) == 0) break;
+            if (fget<B, L::OB, N>(w, row * V + i) == 0) break;
             n++;
         }
         return n;
@@ -98,7 +100,7 @@ template <class L> struct Ops {
     /* ---------------------------------------------------------------- the step function */
     /* candidate groups: the blocks of the cascade below, in Next's textual order */
     static constexpr int NGRP = 13;
-    static VSR_HD int grp_begin(int g) {
+    static VSR_HD constexpr int grp_begin(int g) {
         const int b[NGRP + 1] = {L::C_TIMER, L::C_HSVC, L::C_SDVC, L::C_HDVC, L::C_SSV, L::C_RSV, L::C_CREQ, L::C_RPREP,
                                  L::C_RPOK, L::C_EXEC, L::C_SGS, L::C_RGS, L::C_RNS, L::NCAND};
         return b[g];
@@ -311,7 +313,7 @@ template <class L> struct Ops {
             }
             if (!APPLY) return mult;
             const int req = (int)VGET(L, CT_REQ, s, r) + 1;
-            const int op = loglen<L::LOG_B>(s, r) + 1;
+            const int op = loglen<L::LOG_B, L::LOG_N>(s, r) + 1;
             if (req > V || op > V) return E_OVERFLOW;
             if (run.symmetry) {
                 /* canonical labels: created values ordered by the (view, op_number) of their Prepare */
@@ -360,7 +362,7 @@ template <class L> struct Ops {
             if (VGET(L, STATUS, s, r) != 0) return 0;
             if (pv != (int)VGET(L, VIEWN, s, r)) return 0;
             const int mop = (int)VGET(L, PR_OP, s, x);
-            if (mop != loglen<L::LOG_B>(s, r) + 1) return 0;
+            if (mop != loglen<L::LOG_B, L::LOG_N>(s, r) + 1) return 0;
             if (!APPLY) return 1;
             const int mcn = (int)VGET(L, PR_COMMIT, s, x);
             VSET(L, LOG, n, r * V + (mop - 1), x + 1);
@@ -395,7 +397,7 @@ template <class L> struct Ops {
             if (primary((int)VGET(L, VIEWN, s, r)) != r) return 0;
             if (VGET(L, STATUS, s, r) != 0) return 0;
             const int cn = (int)VGET(L, COMMIT, s, r);
-            if (!(cn < loglen<L::LOG_B>(s, r))) return 0;
+            if (!(cn < loglen<L::LOG_B, L::LOG_N>(s, r))) return 0;
             int q = 0;
             for (int p = 0; p < R; p++) q += (int)VGET(L, PEER, s, r * R + p) >= cn + 1;
             if (!(q >= R / 2)) return 0;
@@ -420,7 +422,7 @@ template <class L> struct Ops {
             if (primary(vr) == r) return 0;
             if (VGET(L, STATUS, s, r) != 0) return 0;
             if (!(pv > vr)) return 0;
-            const int len = loglen<L::LOG_B>(s, r);
+            const int len = loglen<L::LOG_B, L::LOG_N>(s, r);
             if (!((int)VGET(L, PR_OP, s, x) > len + 1)) return 0;
             const int cn = (int)VGET(L, COMMIT, s, r);
             const int t = cn <= len ? cn : len; /* MinVal :307-308 */
@@ -449,7 +451,7 @@ template <class L> struct Ops {
             if ((int)VGET(L, VIEWN, s, r) != v) return 0;
             if (VGET(L, STATUS, s, r) != 0) return 0;
             const int t = (int)VGET(L, GS_T, s, gi);
-            const int len = loglen<L::LOG_B>(s, r);
+            const int len = loglen<L::LOG_B, L::LOG_N>(s, r);
             if (!(len > t)) return 0;
             if (!APPLY) return 1;
             VSET(L, GS_ST, n, gi, ST_CONSUMED);
@@ -468,13 +470,43 @@ template <class L> struct Ops {
             if ((int)VGET(L, VIEWN, s, r) != v) return 0;
             if (VGET(L, STATUS, s, r) != 0) return 0;
             const int t = (int)VGET(L, GS_T, s, gi); /* first_op - 1 */
-            if (loglen<L::LOG_B>(s, r) != t) return 0;
+            if (loglen<L::LOG_B, L::LOG_N>(s, r) != t) return 0;
             if (!APPLY) return 1;
             for (int i = t; i < V; i++) VSET(L, LOG, n, r * V + i, VGET(L, NS_LOG, s, gi * V + i));
             VSET(L, NS_ST, n, gi, ST_CONSUMED);
             return 1;
         }
         return 0;
+    }
+
+    /* Guards of one group on a state whose words are in registers (RegRow): bit i of mask[i / 32] is set iff candidate
+       grp_begin(G) + i is enabled.  The candidate index is a compile-time constant in every guard, so slot decoding,
+       word indices and shifts fold away: a guard is a handful of bit tests on registers.  Same guards as step_grp<false>
+       (it IS step_grp<false>); tests/harness compares the masks with the one-candidate-at-a-time form on the host. */
+    static VSR_HD constexpr int grp_size(int g) { return grp_begin(g + 1) - grp_begin(g); }
+    static VSR_HD constexpr int grp_words(int g) { return (grp_size(g) + 31) / 32; }
+    template <int G, class S, int... I>
+    static VSR_HD void enabled_seq(const RunCfg& run, const S& s, uint32_t* mask, std::integer_sequence<int, I...>) {
+        ((mask[I >> 5] |= (uint32_t)(step_grp<false, G>(run, s, grp_begin(G) + I, (uint32_t*)nullptr) > 0) << (I & 31)), ...);
+    }
+    template <int G, class S> static VSR_HD void enabled_group(const RunCfg& run, const S& s, uint32_t* mask) {
+        enabled_seq<G>(run, s, mask, std::make_integer_sequence<int, grp_size(G)>());
+    }
+
+    /* the enabled candidates of a state, in candidate order, through the register-mask form (host side of the C ABI's
+       vsr_enabled_candidates, which cross-checks it against the one-candidate form) */
+    template <int G> static VSR_HD int list_group(const RunCfg& run, const RegRow<L::NW>& st, uint32_t* out, int n) {
+        uint32_t m[grp_words(G)] = {};
+        enabled_group<G>(run, st, m);
+        for (int i = 0; i < grp_size(G); i++)
+            if ((m[i >> 5] >> (i & 31)) & 1u) out[n++] = (uint32_t)(grp_begin(G) + i);
+        if constexpr (G + 1 < NGRP) return list_group<G + 1>(run, st, out, n);
+        else return n;
+    }
+    static VSR_HD int enabled_list(const RunCfg& run, const uint32_t* w, uint32_t* out /* NCAND entries */) {
+        RegRow<L::NW> st;
+        for (int i = 0; i < L::NW; i++) st.w[i] = w[i];
+        return list_group<0>(run, st, out, 0);
     }
 
     /* action id (VSR_ACT_*, = textual position in Next) of a candidate index */
@@ -678,29 +710,33 @@ inline void fp64_build_slices(uint64_t s8[8 * 256]) {
         }
 }
 
-template <class L, class W> VSR_HD uint64_t fp64_view8(const uint64_t* __restrict__ s8, const W& w, bool use_view) {
+template <class L, bool USE_VIEW, class W> VSR_HD uint64_t fp64_view8_t(const uint64_t* __restrict__ s8, const W& w) {
     static_assert(L::NW % 2 == 0, "whole 64-bit words");
     uint64_t fp = FP64_POLY;
     constexpr int full = L::VIEW_BITS >> 5, rem = L::VIEW_BITS & 31;
     /* bytes of whole zero words after the VIEW prefix are not hashed by the byte form either: hash ceil(nw/2) pairs,
        but an odd word count must not pull in the next word: mask it to zero and stop the byte count there */
-    const int nw = use_view ? (full + (rem ? 1 : 0)) : L::NW;
+    constexpr int nw = USE_VIEW ? (full + (rem ? 1 : 0)) : L::NW;
     int i = 0;
+VSR_UNROLL
     for (; i + 1 < nw; i += 2) {
         uint32_t lo = rdw(w, i), hi = rdw(w, i + 1);
-        if (use_view && i + 1 == full) hi &= (1u << rem) - 1u;
+        if (USE_VIEW && i + 1 == full) hi &= (1u << rem) - 1u;
         const uint64_t y = fp ^ (((uint64_t)hi << 32) | lo);
         fp = s8[7 * 256 + (y & 0xFF)] ^ s8[6 * 256 + ((y >> 8) & 0xFF)] ^ s8[5 * 256 + ((y >> 16) & 0xFF)] ^
              s8[4 * 256 + ((y >> 24) & 0xFF)] ^ s8[3 * 256 + ((y >> 32) & 0xFF)] ^ s8[2 * 256 + ((y >> 40) & 0xFF)] ^
              s8[1 * 256 + ((y >> 48) & 0xFF)] ^ s8[(y >> 56) & 0xFF];
     }
-    if (i < nw) { /* one trailing 32-bit word: four bytes */
-        uint32_t x = rdw(w, i);
-        if (use_view && i == full) x &= (1u << rem) - 1u;
+    if (nw & 1) { /* one trailing 32-bit word: four bytes */
+        uint32_t x = rdw(w, nw - 1);
+        if (USE_VIEW && nw - 1 == full) x &= (1u << rem) - 1u;
         const uint32_t y = x ^ (uint32_t)fp;
         fp = (fp >> 32) ^ s8[3 * 256 + (y & 0xFF)] ^ s8[2 * 256 + ((y >> 8) & 0xFF)] ^ s8[1 * 256 + ((y >> 16) & 0xFF)] ^ s8[(y >> 24) & 0xFF];
     }
     return fp;
+}
+template <class L, class W> VSR_HD uint64_t fp64_view8(const uint64_t* __restrict__ s8, const W& w, bool use_view) {
+    return use_view ? fp64_view8_t<L, true>(s8, w) : fp64_view8_t<L, false>(s8, w);
 }
 
 } // namespace vsr

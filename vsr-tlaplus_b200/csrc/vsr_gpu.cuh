@@ -116,20 +116,24 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) { /* splitmix64 finaliser:
     x ^= x >> 31;
     return x;
 }
-template <class L, class W> VSR_HD uint32_t check_hash(const W& w, bool use_view) {
+template <class L, bool USE_VIEW, class W> VSR_HD uint32_t check_hash_t(const W& w) {
     /* second, independent 32-bit hash of the VIEW words (3 instructions per word + finaliser): lets the seen-set tell
        fp64 collisions apart instead of silently merging two states as a bare fingerprint set would */
     constexpr int full = L::VIEW_BITS >> 5, rem = L::VIEW_BITS & 31;
-    const int nw = use_view ? (full + (rem ? 1 : 0)) : L::NW;
+    constexpr int nw = USE_VIEW ? (full + (rem ? 1 : 0)) : L::NW;
     uint32_t h = 0x9747b28cu;
+VSR_UNROLL
     for (int i = 0; i < nw; i++) {
         uint32_t k = rdw(w, i);
-        if (use_view && i == full) k &= (1u << rem) - 1u;
+        if (USE_VIEW && i == full) k &= (1u << rem) - 1u;
         h ^= k;
         h = ((h << 13) | (h >> 19)) * 5u + 0xe6546b64u;
     }
     h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
     return h;
+}
+template <class L, class W> VSR_HD uint32_t check_hash(const W& w, bool use_view) {
+    return use_view ? check_hash_t<L, true>(w) : check_hash_t<L, false>(w);
 }
 
 enum { INS_NEW = 0, INS_DUP = 1, INS_TIE = 2, INS_FULL = 3 };
@@ -199,8 +203,6 @@ template <class L> struct WarpStage {
        (one copy of each in the instruction cache), and an object whose address is passed to them would be kept in
        local memory — 1024 threads x a few hundred bytes does not fit the L1 left beside 220 KB of shared memory. */
     int sn;                                      /* states currently staged */
-    unsigned int coll, ties;
-    unsigned long long gen, probes;
 };
 template <class L, int WARPS> struct BlockSmemT {
     static constexpr int NS = WARPS * 32;        /* parent states per block round: one per thread */
@@ -292,53 +294,63 @@ template <class L> struct Expander {
        (fewer than 32 states are staged then), rotated by the lane so equal word indices fall in different banks */
     static __device__ __forceinline__ Row scratch(WarpStage<L>& S, int lane) { return Row{&S.stage[(32 + lane) * L::NW], lane % L::NW}; }
 
-    static __device__ __noinline__ void emit(const ExpandParams& P, Smem& B, WarpStage<L>& S, int lane, const Row n, int mult, int cand, int si,
-                                             bool act) {
-        unsigned long long gen = 0;
-        unsigned probes = 0, coll = 0, ties = 0;
+    /* returns this lane's counts for the run's statistics: successors generated (low half) | seen-set probes (high half);
+       the caller keeps the running sums in registers (a warp reduction per batch cost 25 shuffles) */
+    static __device__ __noinline__ unsigned long long emit(const ExpandParams& P, Smem& B, WarpStage<L>& S, int lane, const Row n, int mult,
+                                                           int cand, int si, bool act) {
+        unsigned gen = 0, probes = 0, coll = 0;
         int sn = S.sn;
         int send_to = -1;
         uint64_t s_fp = 0, s_meta = 0, s_parent = 0;
         bool isnew = false;
         int bad = 0;
         unsigned long long trec = 0;
+        /* the successor's words, read once from the lane's scratch row: fingerprint, check hash, aux key, invariant and
+           the copies to the staging area / a peer's send buffer all work on registers (constant word indices) */
+        RegRow<L::NW> v;
+        if (act && mult > 0) {
+            VSR_UNROLL
+            for (int j = 0; j < L::NW; j++) v.w[j] = rdw(n, j);
+        }
         if (act) {
             if (mult < 0) {
                 atomicCAS(&P.ctr->error, 0, mult);
             } else if (mult > 0) {
-                uint64_t fp = fp64_view8<L>(B.fp_tab, n, P.run.use_view != 0);
+                uint64_t fp = fp64_view8<L>(B.fp_tab, v, P.run.use_view != 0);
                 if (fp == 0) fp = 1;
                 const int owner = P.world > 1 ? (int)(fp >> P.owner_shift) : P.rank;
                 /* start the seen-set probe now; the check hash, aux key and tags are computed under its latency */
                 const unsigned long long home = table_home(P.table_mask, fp);
                 ulonglong2 first = make_ulonglong2(0, 0);
                 if (owner == P.rank) first = __ldcg(reinterpret_cast<const ulonglong2*>(P.table + 2 * home));
-                const uint32_t chk = check_hash<L>(n, P.run.use_view != 0);
-                const uint32_t auxkey = O_::aux_key(n);
+                const uint32_t chk = check_hash<L>(v, P.run.use_view != 0);
+                const uint32_t auxkey = O_::aux_key(v);
                 const uint64_t meta = make_meta(P.level, auxkey, chk);
                 const uint64_t parent_gid = make_gid(P.rank, P.in_base + B.round_first + si);
                 trec = make_trec(parent_gid, (uint32_t)cand);
                 if (owner == P.rank) {
-                    gen += (unsigned long long)mult; /* successors sent to a peer are counted where they are inserted */
+                    gen += (unsigned)mult; /* successors sent to a peer are counted where they are inserted */
                     const int r = table_insert_from(P.table, P.table_mask, home, first.x, first.y, fp, meta, probes, coll);
                     isnew = r == INS_NEW;
                     if (r == INS_FULL) atomicExch(&P.ctr->overflow, 4);
-                    if (isnew) bad = O_::invariant(P.run, n);
+                    if (isnew) bad = O_::invariant(P.run, v);
+                    if (coll) atomicAdd(&P.ctr->collisions, (unsigned long long)coll); /* never seen so far */
                     if (r == INS_TIE) {
-                        ties++;
+                        atomicAdd(&P.ctr->ties, 1ull);
                         const unsigned long long t = atomicAdd(&P.ctr->tie_count, 1ull);
                         if (t < P.tie_cap) {
                             TieRec rec;
                             rec.fp = fp; rec.parent = parent_gid; rec.auxkey = auxkey; rec.cand = (uint32_t)cand; rec.check = chk; rec._pad = 0;
                             uint8_t* dst = P.ties + t * (sizeof(TieRec) + L::BYTES);
                             *(TieRec*)dst = rec;
-                            for (int j = 0; j < L::NW; j++) ((uint32_t*)(dst + sizeof(TieRec)))[j] = rdw(n, j);
+                            VSR_UNROLL
+                            for (int j = 0; j < L::NW; j++) ((uint32_t*)(dst + sizeof(TieRec)))[j] = v.w[j];
                         } else atomicExch(&P.ctr->overflow, 2);
                     }
                 } else if (P.sent_cache && P.sent_cache[mix64(fp ^ auxkey) & P.sent_mask] == (fp ^ ((uint64_t)auxkey << 40))) {
                     /* this exact (VIEW, aux) pair was already shipped to its owner earlier in the run: a duplicate for
                        sure, so it is counted here and not sent again (most generated successors are duplicates) */
-                    gen += (unsigned long long)mult;
+                    gen += (unsigned)mult;
                 } else {
                     if (P.sent_cache) P.sent_cache[mix64(fp ^ auxkey) & P.sent_mask] = fp ^ ((uint64_t)auxkey << 40);
                     send_to = owner;
@@ -360,23 +372,21 @@ template <class L> struct Expander {
                 if (idx < P.send_cap) {
                     uint8_t* rec = P.send + ((size_t)send_to * P.send_cap + idx) * (L::BYTES + sizeof(RecHdr));
                     uint32_t* rw = (uint32_t*)rec;
-                    for (int j = 0; j < L::NW; j++) rw[j] = rdw(n, j);
+                    VSR_UNROLL
+                    for (int j = 0; j < L::NW; j++) rw[j] = v.w[j];
                     RecHdr* h = (RecHdr*)(rec + L::BYTES);
                     h->fp = s_fp; h->meta = s_meta; h->parent = s_parent; h->cand = (uint32_t)cand; h->mult = (uint32_t)mult;
                 } else atomicExch(&P.ctr->overflow, 3);
             }
         }
-        /* compaction of the survivors into the warp's staging area (one ballot, all lanes) */
+        /* compaction of the survivors into the warp's staging area (one ballot, all lanes).  The survivors' final rows
+           may overlap other lanes' scratch rows: every lane has read its row (above) before anybody writes */
         const unsigned newmask = __ballot_sync(0xffffffffu, isnew);
-        /* the survivors' final rows may overlap other lanes' scratch rows: everybody reads first, then writes */
-        uint32_t v[L::NW];
-        if (isnew) {
-            for (int j = 0; j < L::NW; j++) v[j] = rdw(n, j);
-        }
         __syncwarp();
         if (isnew) {
             const int slot = sn + __popc(newmask & ((1u << lane) - 1u));
-            for (int j = 0; j < L::NW; j++) S.stage[slot * L::NW + j] = v[j];
+            VSR_UNROLL
+            for (int j = 0; j < L::NW; j++) S.stage[slot * L::NW + j] = v.w[j];
             if (bad) {
                 trec |= 1ull << 63;
                 atomicOr(&P.ctr->viol_which, bad);
@@ -384,28 +394,17 @@ template <class L> struct Expander {
             S.tstage[slot] = trec;
         }
         sn += __popc(newmask);
-        /* per-warp totals of this batch */
-        for (int o = 16; o; o >>= 1) {
-            gen += __shfl_xor_sync(0xffffffffu, gen, o);
-            probes += __shfl_xor_sync(0xffffffffu, probes, o);
-            coll += __shfl_xor_sync(0xffffffffu, coll, o);
-            ties += __shfl_xor_sync(0xffffffffu, ties, o);
-        }
         __syncwarp();
-        if (lane == 0) {
-            S.sn = sn;
-            S.gen += gen;
-            S.probes += probes;
-            S.coll += coll;
-            S.ties += ties;
-        }
+        if (lane == 0) S.sn = sn;
         __syncwarp();
         while (sn >= 32) {
             flush(P, S, lane, 32);
             sn -= 32;
         }
+        return (unsigned long long)gen | ((unsigned long long)probes << 32);
     }
 
+#ifdef VSR_SCAN_V1
     /* scan one action group: guards only; enabled pairs go to the block pool */
     template <int G> __device__ __forceinline__ void scan() {
         const int c0 = O_::grp_begin(G), c1 = O_::grp_begin(G + 1);
@@ -424,9 +423,7 @@ template <class L> struct Expander {
                 const int pos = base + __popc(en & ((1u << lane) - 1u));
                 const bool inl = m > 0 && pos >= Smem::QCAP;
                 if (m > 0 && !inl) B.pool[pos] = (uint16_t)(tid | ((cand - c0) << 9));
-                if (__any_sync(0xffffffffu, inl)) {
-                    apply<G>(P, B, S, lane, mine, cand, tid, inl);
-                }
+                if (__any_sync(0xffffffffu, inl)) tally(apply<G>(P, B, S, lane, mine, cand, tid, inl));
             }
         }
         /* every warp does the same amount of scan work, so this barrier is cheap; after it qcount[G] is final and the
@@ -434,16 +431,125 @@ template <class L> struct Expander {
         __syncthreads();
         gbase = gbase + B.qcount[G] < Smem::QCAP ? gbase + B.qcount[G] : Smem::QCAP;
     }
+#else
+    /* ---- scan: guards only, from registers.  Each thread copies its own state into registers and evaluates every guard
+       of Next on it with compile-time candidate indices (Ops::enabled_group): a guard is a few bit tests on registers,
+       not a decode of a run-time slot index plus shared-memory reads.  The result is one bit per candidate.  Then the
+       (state, candidate) pairs are laid out in the block pool grouped by action: per-lane counts -> one packed warp
+       prefix sum -> one shared atomic per (warp, group) -> barrier -> each lane writes its own pairs.  Two barriers per
+       round instead of one per group. */
+    static constexpr int NG = O_::NGRP;
+    static __host__ __device__ constexpr int moff(int g) { int o = 0; for (int h = 0; h < g; h++) o += O_::grp_words(h); return o; }
+    static constexpr int MW = moff(NG);       /* mask words per state */
+    static constexpr int PW = (NG + 1) / 2;   /* packed 16-bit counters, two groups per word */
+    static __host__ __device__ constexpr int max_grp() { int m = 0; for (int g = 0; g < NG; g++) m = O_::grp_size(g) > m ? O_::grp_size(g) : m; return m; }
+    static_assert(max_grp() < 128 && NS <= 512, "pool item = thread (9 bits) | candidate offset in its group (7 bits)");
+    static_assert(max_grp() * NS < 65536, "16-bit packed counters");
+
+    template <int G> __device__ __forceinline__ void guards(const RegRow<L::NW>& st, uint32_t* m, uint32_t* pc) {
+        O_::template enabled_group<G>(P.run, st, m + moff(G));
+        uint32_t c = 0;
+        VSR_UNROLL
+        for (int k = 0; k < O_::grp_words(G); k++) c += (uint32_t)__popc(m[moff(G) + k]);
+        pc[G >> 1] += c << (16 * (G & 1));
+        if constexpr (G + 1 < NG) guards<G + 1>(st, m, pc);
+    }
+    /* write this lane's pairs of group G (and the following groups) to the pool; pairs that do not fit stay in m */
+    template <int G> __device__ __forceinline__ void push(uint32_t* m, const uint32_t* ex, const uint32_t* wb, int st) {
+        int pos = st + (int)((wb[G >> 1] >> (16 * (G & 1))) & 0xFFFFu) + (int)((ex[G >> 1] >> (16 * (G & 1))) & 0xFFFFu);
+        VSR_UNROLL
+        for (int k = 0; k < O_::grp_words(G); k++) {
+            uint32_t mm = m[moff(G) + k], left = 0;
+            while (mm) {
+                const int bit = __ffs(mm) - 1;
+                mm &= mm - 1;
+                if (pos < Smem::QCAP) B.pool[pos] = (uint16_t)(tid | ((k * 32 + bit) << 9));
+                else left |= 1u << bit;
+                pos++;
+            }
+            m[moff(G) + k] = left;
+        }
+        if constexpr (G + 1 < NG) {
+            const int nst = st + B.qcount[G] < Smem::QCAP ? st + B.qcount[G] : Smem::QCAP;
+            push<G + 1>(m, ex, wb, nst);
+        }
+    }
+    /* pool full (rare): the pairs left in m are applied right here by their own lanes, one group at a time */
+    template <int G> __device__ __forceinline__ void leftovers(uint32_t* m) {
+        VSR_UNROLL
+        for (int k = 0; k < O_::grp_words(G); k++) {
+            while (__any_sync(0xffffffffu, m[moff(G) + k] != 0)) {
+                const bool inl = m[moff(G) + k] != 0;
+                int cand = 0;
+                if (inl) {
+                    const int bit = __ffs(m[moff(G) + k]) - 1;
+                    m[moff(G) + k] &= m[moff(G) + k] - 1;
+                    cand = O_::grp_begin(G) + k * 32 + bit;
+                }
+                tally(apply<G>(P, B, S, lane, mine, cand, tid, inl));
+            }
+        }
+        if constexpr (G + 1 < NG) leftovers<G + 1>(m);
+    }
+    __device__ __forceinline__ void scan_all() {
+        uint32_t m[MW], pc[PW];
+        VSR_UNROLL
+        for (int i = 0; i < MW; i++) m[i] = 0;
+        VSR_UNROLL
+        for (int i = 0; i < PW; i++) pc[i] = 0;
+        if (have) {
+            RegRow<L::NW> st;
+            VSR_UNROLL
+            for (int i = 0; i < L::NW; i++) st.w[i] = mine[i];
+            guards<0>(st, m, pc);
+        }
+        /* warp prefix sums of the per-lane counts, two groups per word */
+        uint32_t ex[PW], wb[PW];
+        VSR_UNROLL
+        for (int i = 0; i < PW; i++) ex[i] = pc[i];
+        VSR_UNROLL
+        for (int o = 1; o < 32; o <<= 1) {
+            VSR_UNROLL
+            for (int i = 0; i < PW; i++) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, ex[i], o);
+                if (lane >= o) ex[i] += t;
+            }
+        }
+        /* lane g reserves the warp's share of group g's pool segment */
+        uint32_t mytot = 0, anyc = 0;
+        VSR_UNROLL
+        for (int g = 0; g < NG; g++) {
+            const uint32_t t = (__shfl_sync(0xffffffffu, ex[g >> 1], 31) >> (16 * (g & 1))) & 0xFFFFu;
+            if (lane == g) mytot = t;
+        }
+        VSR_UNROLL
+        for (int i = 0; i < PW; i++) { anyc |= pc[i]; ex[i] -= pc[i]; } /* inclusive -> exclusive */
+        uint32_t mybase = 0;
+        if (lane < NG && mytot) mybase = (uint32_t)atomicAdd(&B.qcount[lane], (int)mytot);
+        VSR_UNROLL
+        for (int i = 0; i < PW; i++) wb[i] = 0;
+        VSR_UNROLL
+        for (int g = 0; g < NG; g++) wb[g >> 1] |= (__shfl_sync(0xffffffffu, mybase, g) & 0xFFFFu) << (16 * (g & 1));
+        if (P.check_deadlock && have && !anyc) atomicMin(&P.ctr->dead_id, P.in_base + B.round_first + tid);
+        __syncthreads(); /* qcount[] final: group g's segment starts at min(sum of the groups before it, QCAP) */
+        push<0>(m, ex, wb, 0);
+        uint32_t rest = 0;
+        VSR_UNROLL
+        for (int i = 0; i < MW; i++) rest |= m[i];
+        if (__any_sync(0xffffffffu, rest != 0)) leftovers<0>(m);
+    }
+#endif
     /* apply one (parent, candidate) pair of group G per lane; the only copy of that action's effect in the kernel */
-    template <int G> static __device__ __noinline__ void apply(const ExpandParams& P, Smem& B, WarpStage<L>& S, int lane, const uint32_t* parent,
-                                                               int cand, int si, bool act) {
+    template <int G> static __device__ __noinline__ unsigned long long apply(const ExpandParams& P, Smem& B, WarpStage<L>& S, int lane,
+                                                                             const uint32_t* parent, int cand, int si, bool act) {
         const Row n = scratch(S, lane);
         int mult = 0;
         if (act) mult = O_::template step_grp<true, G>(P.run, parent, cand, n);
-        emit(P, B, S, lane, n, mult, cand, si, act);
+        return emit(P, B, S, lane, n, mult, cand, si, act);
     }
     /* one batch of <= 32 queued pairs of group G, pool[b .. b + k) */
-    template <int G> static __device__ __forceinline__ void batch(const ExpandParams& P, Smem& B, WarpStage<L>& S, int lane, int b, int k) {
+    template <int G> static __device__ __forceinline__ unsigned long long batch(const ExpandParams& P, Smem& B, WarpStage<L>& S, int lane, int b,
+                                                                                int k) {
         const bool act = lane < k;
         int cand = 0, si = 0;
         if (act) {
@@ -451,7 +557,12 @@ template <class L> struct Expander {
             si = item & 511;
             cand = O_::grp_begin(G) + (int)(item >> 9);
         }
-        apply<G>(P, B, S, lane, &B.par[si * (L::NW + 1)], cand, si, act);
+        return apply<G>(P, B, S, lane, &B.par[si * (L::NW + 1)], cand, si, act);
+    }
+    unsigned long long acc_gen = 0, acc_probes = 0; /* this lane's share of the statistics, summed over the launch */
+    __device__ __forceinline__ void tally(unsigned long long r) {
+        acc_gen += (unsigned)r;
+        acc_probes += r >> 32;
     }
 
     __device__ void run_round(unsigned long long first, int count) {
@@ -464,53 +575,65 @@ template <class L> struct Expander {
         __syncthreads();
         have = tid < count;
         mine = &B.par[(have ? tid : 0) * (L::NW + 1)];
+#ifdef VSR_SCAN_V1
         any = false;
         scan<0>(); scan<1>(); scan<2>(); scan<3>(); scan<4>(); scan<5>(); scan<6>();
         scan<7>(); scan<8>(); scan<9>(); scan<10>(); scan<11>(); scan<12>();
         if (P.check_deadlock && have && !any) atomicMin(&P.ctr->dead_id, P.in_base + first + tid);
+#else
+        scan_all();
+#endif
         __syncthreads();
-        /* batches: group g has ceil(|group g's pool segment| / 32) of them */
-        int total = 0;
-        {
-            int st = 0;
-            for (int g = 0; g < Smem::NG; g++) {
-                const int en = st + B.qcount[g] < Smem::QCAP ? st + B.qcount[g] : Smem::QCAP;
-                total += (en - st + 31) >> 5;
-                st = en;
-            }
+        /* batches: group g has ceil(|group g's pool segment| / 32) of them.  Lane g keeps group g's segment [st, en) and
+           the index of its first batch, so mapping a batch number to (group, offset) is one ballot and three shuffles. */
+        const int q = lane < Smem::NG ? B.qcount[lane] : 0;
+        int inc = q;
+        VSR_UNROLL
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
         }
+        const int seg_st = inc - q < Smem::QCAP ? inc - q : Smem::QCAP, seg_en = inc < Smem::QCAP ? inc : Smem::QCAP;
+        const int nb = (seg_en - seg_st + 31) >> 5;
+        int binc = nb;
+        VSR_UNROLL
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, binc, o);
+            if (lane >= o) binc += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, binc, 31);
         for (;;) {
             int t = 0;
             if (lane == 0) t = atomicAdd(&B.take, 1);
             t = __shfl_sync(0xffffffffu, t, 0);
             if (t >= total) break;
-            int g = 0, st = 0, en = 0;
-            for (;; g++) { /* which group does batch t belong to, and where does that group's segment start */
-                en = st + B.qcount[g] < Smem::QCAP ? st + B.qcount[g] : Smem::QCAP;
-                const int nbg = (en - st + 31) >> 5;
-                if (t < nbg) break;
-                t -= nbg;
-                st = en;
-            }
-            const int b = st + t * 32;
+            const int g = __popc(__ballot_sync(0xffffffffu, lane < Smem::NG && binc <= t)); /* groups that end before batch t */
+            const int st = __shfl_sync(0xffffffffu, seg_st, g), en = __shfl_sync(0xffffffffu, seg_en, g);
+            const int b = st + (t - __shfl_sync(0xffffffffu, binc - nb, g)) * 32;
             const int k = en - b < 32 ? en - b : 32;
+            unsigned long long r;
             switch (g) {
-            case 0: batch<0>(P, B, S, lane, b, k); break;   case 1: batch<1>(P, B, S, lane, b, k); break;   case 2: batch<2>(P, B, S, lane, b, k); break;
-            case 3: batch<3>(P, B, S, lane, b, k); break;   case 4: batch<4>(P, B, S, lane, b, k); break;   case 5: batch<5>(P, B, S, lane, b, k); break;
-            case 6: batch<6>(P, B, S, lane, b, k); break;   case 7: batch<7>(P, B, S, lane, b, k); break;   case 8: batch<8>(P, B, S, lane, b, k); break;
-            case 9: batch<9>(P, B, S, lane, b, k); break;   case 10: batch<10>(P, B, S, lane, b, k); break; case 11: batch<11>(P, B, S, lane, b, k); break;
-            default: batch<12>(P, B, S, lane, b, k); break;
+            case 0: r = batch<0>(P, B, S, lane, b, k); break;   case 1: r = batch<1>(P, B, S, lane, b, k); break;
+            case 2: r = batch<2>(P, B, S, lane, b, k); break;   case 3: r = batch<3>(P, B, S, lane, b, k); break;
+            case 4: r = batch<4>(P, B, S, lane, b, k); break;   case 5: r = batch<5>(P, B, S, lane, b, k); break;
+            case 6: r = batch<6>(P, B, S, lane, b, k); break;   case 7: r = batch<7>(P, B, S, lane, b, k); break;
+            case 8: r = batch<8>(P, B, S, lane, b, k); break;   case 9: r = batch<9>(P, B, S, lane, b, k); break;
+            case 10: r = batch<10>(P, B, S, lane, b, k); break; case 11: r = batch<11>(P, B, S, lane, b, k); break;
+            default: r = batch<12>(P, B, S, lane, b, k); break;
             }
+            tally(r);
         }
     }
 
     __device__ void finish() {
         while (S.sn > 0) flush(P, S, lane, S.sn < 32 ? S.sn : 32);
+        for (int o = 16; o; o >>= 1) {
+            acc_gen += __shfl_xor_sync(0xffffffffu, acc_gen, o);
+            acc_probes += __shfl_xor_sync(0xffffffffu, acc_probes, o);
+        }
         if (lane == 0) {
-            atomicAdd(&P.ctr->generated, S.gen);
-            atomicAdd(&P.ctr->probes, S.probes);
-            if (S.coll) atomicAdd(&P.ctr->collisions, (unsigned long long)S.coll);
-            if (S.ties) atomicAdd(&P.ctr->ties, (unsigned long long)S.ties);
+            atomicAdd(&P.ctr->generated, acc_gen);
+            atomicAdd(&P.ctr->probes, acc_probes);
         }
     }
 };
@@ -524,7 +647,7 @@ template <class L> __global__ void __launch_bounds__(ExpandCfg<L>::WARPS * 32, 2
     Expander<L> X(P, B);
     if ((threadIdx.x & 31) == 0) {
         WarpStage<L>& S = B.w[threadIdx.x >> 5];
-        S.sn = 0; S.coll = 0; S.ties = 0; S.gen = 0; S.probes = 0;
+        S.sn = 0;
     }
     const unsigned long long nrounds = (P.n_in + Smem::NS - 1) / Smem::NS;
     if (threadIdx.x == 0) next_round = atomicAdd(&P.ctr->work_next, 1ull);

@@ -30,6 +30,7 @@ template <class L> struct Thunks {
     static int invariant(const RunCfg* run, const uint32_t* w) { return Ops<L>::invariant(*run, w); }
     static uint64_t fingerprint(const uint32_t* w, int use_view) { return fp64_view8<L>(fp64_table(), w, use_view != 0); }
     static int random_enabled(const RunCfg* run, const uint32_t* s, uint64_t* rng) { return Ops<L>::random_enabled(*run, s, *rng); }
+    static int enabled_list(const RunCfg* run, const uint32_t* s, uint32_t* out) { return Ops<L>::enabled_list(*run, s, out); }
     static uint64_t fingerprint_bytewise(const uint32_t* w, int use_view) { return fp64_view<L>(fp64_table(), w, use_view != 0); }
     static uint32_t aux_key(const uint32_t* w) { return Ops<L>::aux_key(w); }
     static int canon(uint32_t* w) { return Ops<L>::canonicalize(w); }
@@ -38,7 +39,7 @@ template <class L> struct Thunks {
     static int literal_cand(const uint32_t* w, int cand) { return Ops<L>::literal_cand(w, cand); }
     static const ModelOps* get() {
         static const ModelOps ops = {L::R, L::V, L::K, L::NW, L::BYTES, L::TOTAL_BITS, L::NCAND, init, step, guard,
-                                     action_of, invariant, fingerprint, aux_key, canon, unpack, pack, literal_cand, fingerprint_bytewise, random_enabled};
+                                     action_of, invariant, fingerprint, aux_key, canon, unpack, pack, literal_cand, fingerprint_bytewise, random_enabled, enabled_list};
         return &ops;
     }
 };
@@ -701,13 +702,19 @@ int vsr_successors(const VsrModel* m, const void* state, void* out, size_t cap, 
 }
 
 int vsr_enabled_candidates(const VsrModel* m, const void* state, uint32_t* out, size_t cap) {
+    /* Two forms of the same guards: one candidate at a time on the packed words (what vsr_successors and the kernel's
+       apply step use), and all candidates of a group at once on a register copy of the state (what the kernel's scan
+       uses).  Both are evaluated here and must agree; -100 says they do not (a bug in the lowering, never expected). */
+    std::vector<uint32_t> fast((size_t)m->ops->ncand);
+    const int nf = m->ops->enabled_list(&m->run, (const uint32_t*)state, fast.data());
     int n = 0;
     for (int c = 0; c < m->ops->ncand; c++) {
         if (!m->ops->guard(&m->run, (const uint32_t*)state, c)) continue;
+        if (n >= nf || fast[(size_t)n] != (uint32_t)c) return -100;
         if ((size_t)n < cap) out[n] = (uint32_t)c;
         n++;
     }
-    return n;
+    return n == nf ? n : -100;
 }
 
 int vsr_canon(const VsrModel* m, void* s) { return m->run.symmetry ? m->ops->canon((uint32_t*)s) : 0; }

@@ -29,8 +29,10 @@
 
 #if defined(__CUDACC__)
 #define VSR_HD __host__ __device__ __forceinline__
+#define VSR_UNROLL _Pragma("unroll")
 #else
 #define VSR_HD inline
+#define VSR_UNROLL
 #endif
 
 namespace vsr {
@@ -164,17 +166,33 @@ template <int NW> VSR_HD void wrw(const SwzRow<NW>& w, int i, uint32_t v) {
     w.base[x] = v;
 }
 
-/* --- element access (base, width compile-time; index run-time) */
-template <int B, int W, class S> VSR_HD uint32_t fget(const S& w, int idx) {
+/* A state held in registers (the expand kernel's guard scan).  A register array cannot be indexed at run time, so a
+   read names the words it may touch — [LO, HI], known from the field's base, width and element count — and selects
+   among them; with a compile-time index (the scan is fully unrolled) the chain folds to the one register. */
+template <int NW> struct RegRow {
+    uint32_t w[NW];
+};
+template <int LO, int HI, class S> VSR_HD uint32_t rdwr(const S& w, int i) { return rdw(w, i); }
+template <int LO, int HI, int NW> VSR_HD uint32_t rdwr(const RegRow<NW>& r, int i) {
+    constexpr int lo = HI < 0 ? 0 : LO, hi = HI < 0 ? NW - 1 : (HI < NW ? HI : NW - 1);
+    uint32_t v = r.w[lo];
+VSR_UNROLL
+    for (int k = lo + 1; k <= hi; k++) v = i == k ? r.w[k] : v;
+    return v;
+}
+template <int NW> VSR_HD uint32_t rdw(const RegRow<NW>& r, int i) { return rdwr<0, -1>(r, i); }
+
+/* --- element access (base, width and element count compile-time; index run-time).  N = 0: count not given. */
+template <int B, int W, int N = 0, class S> VSR_HD uint32_t fget(const S& w, int idx) {
     const int b = B + idx * W;
-    return (rdw(w, b >> 5) >> (b & 31)) & ((1u << W) - 1u);
+    return (rdwr<(B >> 5), (N > 0 ? ((B + W * N - 1) >> 5) : -1)>(w, b >> 5) >> (b & 31)) & ((1u << W) - 1u);
 }
 template <int B, int W, class S> VSR_HD void fset(const S& w, int idx, uint32_t val) {
     const int b = B + idx * W;
     const uint32_t m = ((1u << W) - 1u) << (b & 31);
     wrw(w, b >> 5, (rdw(w, b >> 5) & ~m) | ((val << (b & 31)) & m));
 }
-#define VGET(Lt, F, w, i) ::vsr::fget<Lt::F##_B, Lt::F##_W>((w), (i))
+#define VGET(Lt, F, w, i) ::vsr::fget<Lt::F##_B, Lt::F##_W, Lt::F##_N>((w), (i))
 #define VSET(Lt, F, w, i, v) ::vsr::fset<Lt::F##_B, Lt::F##_W>((w), (i), (uint32_t)(v))
 
 } // namespace vsr
