@@ -228,13 +228,15 @@ template <class L> struct ExpandCfg {
 
 /*
  * Block-synchronous scan, action-pure apply.  A block takes NS = 32*WARPS frontier states (one per thread):
- *   scan   all warps walk Next's action groups in textual order together; each thread evaluates every guard on its
- *          own state and pushes enabled (state, candidate) pairs to that GROUP's queue (one shared-memory atomic per
- *          warp ballot).  Everybody runs the same few kB of guard code at the same time.
- *   apply  after one barrier, warps take batches of 32 pairs of ONE group and apply them one per lane: no
+ *   scan   every thread copies its own state into registers and evaluates all of Next's guards on it with compile-time
+ *          candidate indices: one bit per (action, binding).  The enabled (state, candidate) pairs are then laid out in
+ *          a block pool grouped by action (packed warp prefix sums, one shared atomic per warp and group, one barrier).
+ *   apply  after the second barrier, warps take batches of 32 pairs of ONE group and apply them one per lane: no
  *          divergence between actions inside a warp, full lanes except one partial batch per group.
- * (The first version let every warp walk guards and effects on its own: 88 kB of SASS against a 32 kB instruction
- * cache gave 55 % `no_instruction` stall samples.  A version with a barrier per group starved on barriers instead.)
+ * History, all measured on the shipped VSR.cfg (profiles/round1_expand_kernel.md): (1) every warp walking guards and
+ * effects on its own: 88 kB of SASS against the instruction cache, 55 % `no_instruction` stall samples; (2) guards in a
+ * run-time loop over candidates with one ballot + barrier per group: 75 warp instructions per (32 states, candidate)
+ * for slot decoding and shared-memory field reads; (3) this form: 16 per candidate, 46 % fewer instructions overall.
  */
 template <class L> struct Expander {
     typedef Ops<L> O_;
@@ -244,9 +246,8 @@ template <class L> struct Expander {
     Smem& B;
     WarpStage<L>& S;
     const int lane, warp, tid;
-    int gbase = 0;
     const uint32_t* mine = nullptr;
-    bool have = false, any = false;
+    bool have = false;
 
     __device__ Expander(const ExpandParams& p, Smem& b) : P(p), B(b), S(b.w[threadIdx.x >> 5]), lane(threadIdx.x & 31), warp(threadIdx.x >> 5), tid(threadIdx.x) {}
 
@@ -404,34 +405,6 @@ template <class L> struct Expander {
         return (unsigned long long)gen | ((unsigned long long)probes << 32);
     }
 
-#ifdef VSR_SCAN_V1
-    /* scan one action group: guards only; enabled pairs go to the block pool */
-    template <int G> __device__ __forceinline__ void scan() {
-        const int c0 = O_::grp_begin(G), c1 = O_::grp_begin(G + 1);
-#pragma unroll 1
-        for (int cand = c0; cand < c1; cand++) {
-            int m = 0;
-            if (have) m = O_::template step_grp<false, G>(P.run, mine, cand, (uint32_t*)nullptr);
-            const unsigned en = __ballot_sync(0xffffffffu, m > 0);
-            if (en) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&B.qcount[G], __popc(en));
-                base = gbase + __shfl_sync(0xffffffffu, base, 0);
-                if (m > 0) any = true;
-                /* positions below QCAP are queued; the rest (pool full: rare) are applied right here by their own lanes.
-                   The counter only grows, so a position is either queued by exactly one lane or nobody's. */
-                const int pos = base + __popc(en & ((1u << lane) - 1u));
-                const bool inl = m > 0 && pos >= Smem::QCAP;
-                if (m > 0 && !inl) B.pool[pos] = (uint16_t)(tid | ((cand - c0) << 9));
-                if (__any_sync(0xffffffffu, inl)) tally(apply<G>(P, B, S, lane, mine, cand, tid, inl));
-            }
-        }
-        /* every warp does the same amount of scan work, so this barrier is cheap; after it qcount[G] is final and the
-           next group's pool segment starts where this one ends */
-        __syncthreads();
-        gbase = gbase + B.qcount[G] < Smem::QCAP ? gbase + B.qcount[G] : Smem::QCAP;
-    }
-#else
     /* ---- scan: guards only, from registers.  Each thread copies its own state into registers and evaluates every guard
        of Next on it with compile-time candidate indices (Ops::enabled_group): a guard is a few bit tests on registers,
        not a decode of a run-time slot index plus shared-memory reads.  The result is one bit per candidate.  Then the
@@ -538,7 +511,6 @@ template <class L> struct Expander {
         for (int i = 0; i < MW; i++) rest |= m[i];
         if (__any_sync(0xffffffffu, rest != 0)) leftovers<0>(m);
     }
-#endif
     /* apply one (parent, candidate) pair of group G per lane; the only copy of that action's effect in the kernel */
     template <int G> static __device__ __noinline__ unsigned long long apply(const ExpandParams& P, Smem& B, WarpStage<L>& S, int lane,
                                                                              const uint32_t* parent, int cand, int si, bool act) {
@@ -571,18 +543,10 @@ template <class L> struct Expander {
         for (int i = tid; i < count * L::NW; i += NS) B.par[(i / L::NW) * (L::NW + 1) + (i % L::NW)] = __ldg(src + i);
         if (tid < Smem::NG) B.qcount[tid] = 0;
         if (tid == 0) { B.round_first = first; B.take = 0; }
-        gbase = 0;
         __syncthreads();
         have = tid < count;
         mine = &B.par[(have ? tid : 0) * (L::NW + 1)];
-#ifdef VSR_SCAN_V1
-        any = false;
-        scan<0>(); scan<1>(); scan<2>(); scan<3>(); scan<4>(); scan<5>(); scan<6>();
-        scan<7>(); scan<8>(); scan<9>(); scan<10>(); scan<11>(); scan<12>();
-        if (P.check_deadlock && have && !any) atomicMin(&P.ctr->dead_id, P.in_base + first + tid);
-#else
         scan_all();
-#endif
         __syncthreads();
         /* batches: group g has ceil(|group g's pool segment| / 32) of them.  Lane g keeps group g's segment [st, en) and
            the index of its first batch, so mapping a batch number to (group, offset) is one ballot and three shuffles. */
