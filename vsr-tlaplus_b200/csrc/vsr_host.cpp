@@ -8,41 +8,26 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <dlfcn.h>
+#include <fcntl.h>
+#include <sys/file.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <fstream>
 #include <map>
 #include <sstream>
+#include <mutex>
 #include <string>
+#include <tuple>
 #include <vector>
 
-#include "vsr_flat_conv.h"
-#include "vsr_model.h"
+#include "vsr_thunks.h"
 
 namespace vsr {
 
 /* ------------------------------------------------------------------ layout registry */
-
-template <class L> struct Thunks {
-    static void init(uint32_t* w) { Ops<L>::init(w); }
-    static int step(const RunCfg* run, const uint32_t* s, int cand, uint32_t* n) { return Ops<L>::template step<true>(*run, s, cand, n); }
-    static int guard(const RunCfg* run, const uint32_t* s, int cand) { return Ops<L>::template step<false>(*run, s, cand, nullptr); }
-    static int action_of(int cand) { return Ops<L>::action_of(cand); }
-    static int invariant(const RunCfg* run, const uint32_t* w) { return Ops<L>::invariant(*run, w); }
-    static uint64_t fingerprint(const uint32_t* w, int use_view) { return fp64_view8<L>(fp64_table(), w, use_view != 0); }
-    static int random_enabled(const RunCfg* run, const uint32_t* s, uint64_t* rng) { return Ops<L>::random_enabled(*run, s, *rng); }
-    static int enabled_list(const RunCfg* run, const uint32_t* s, uint32_t* out) { return Ops<L>::enabled_list(*run, s, out); }
-    static uint64_t fingerprint_bytewise(const uint32_t* w, int use_view) { return fp64_view<L>(fp64_table(), w, use_view != 0); }
-    static uint32_t aux_key(const uint32_t* w) { return Ops<L>::aux_key(w); }
-    static int canon(uint32_t* w) { return Ops<L>::canonicalize(w); }
-    static int unpack(const uint32_t* w, VsrFlatState* f) { return Conv<L>::unpack(w, f); }
-    static int pack(const VsrFlatState* f, uint32_t* w, int sym) { return Conv<L>::pack(f, w, sym != 0); }
-    static int literal_cand(const uint32_t* w, int cand) { return Ops<L>::literal_cand(w, cand); }
-    static const ModelOps* get() {
-        static const ModelOps ops = {L::R, L::V, L::K, L::NW, L::BYTES, L::TOTAL_BITS, L::NCAND, init, step, guard,
-                                     action_of, invariant, fingerprint, aux_key, canon, unpack, pack, literal_cand, fingerprint_bytewise, random_enabled, enabled_list};
-        return &ops;
-    }
-};
 
 const ModelOps* find_model_ops(int R, int V, int K) {
 #define X(r, v, k) \
@@ -52,11 +37,101 @@ const ModelOps* find_model_ops(int R, int V, int K) {
     return nullptr;
 }
 
-const uint64_t* fp64_table() {
-    static uint64_t tab[8 * 256]; /* slicing-by-8 tables; the first 256 entries are the byte table */
-    static bool built = false;
-    if (!built) { fp64_build_slices(tab); built = true; }
-    return tab;
+/* ------------------------------------------------------------------ layout plug-ins
+ * Constants outside VSR_FOR_EACH_CONFIG: <dir of this library>/layouts/libvsr_layout_R_V_K.so, compiled on first use from
+ * <dir>/csrc/vsr_layout_plugin.cu when nvcc is there (VSR_B200_JIT=0 forbids compiling; VSR_B200_NVCC names the compiler).
+ * Ranks of one job serialise on a lock file, so one of them compiles and the others load the result. */
+
+struct LayoutPlugin {
+    const ModelOps* ops;
+    const GpuOps* gpu;
+};
+static std::mutex g_plugin_mu;
+static std::map<std::tuple<int, int, int>, LayoutPlugin> g_plugins;
+
+static std::string library_dir() {
+    Dl_info di;
+    if (!dladdr((void*)&find_model_ops, &di) || !di.dli_fname) return ".";
+    std::string p = di.dli_fname;
+    const size_t s = p.rfind('/');
+    return s == std::string::npos ? "." : p.substr(0, s);
+}
+static time_t mtime_of(const std::string& p) {
+    struct stat st;
+    return stat(p.c_str(), &st) == 0 ? st.st_mtime : 0;
+}
+static bool try_open_plugin(const std::string& path, int R, int V, int K, LayoutPlugin* out, std::string& why) {
+    void* h = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
+    if (!h) { why = std::string("dlopen failed: ") + dlerror(); return false; }
+    typedef int (*abi_fn)(void);
+    typedef const ModelOps* (*ops_fn)(void);
+    typedef const GpuOps* (*gpu_fn)(void);
+    abi_fn abi = (abi_fn)dlsym(h, "vsr_plugin_abi");
+    ops_fn ops = (ops_fn)dlsym(h, "vsr_plugin_model_ops");
+    gpu_fn gpu = (gpu_fn)dlsym(h, "vsr_plugin_gpu_ops");
+    if (!abi || !ops || !gpu || abi() != VSR_PLUGIN_ABI) {
+        why = "built against another version of the library";
+        dlclose(h);
+        return false;
+    }
+    const ModelOps* o = ops();
+    if (o->R != R || o->V != V || o->K != K) { why = "holds another layout"; dlclose(h); return false; }
+    out->ops = o;
+    out->gpu = gpu();
+    return true; /* stays loaded for the life of the process: models point into it */
+}
+static bool load_layout_plugin(int R, int V, int K, LayoutPlugin* out, std::string& why) {
+    std::lock_guard<std::mutex> guard(g_plugin_mu);
+    const auto key = std::make_tuple(R, V, K);
+    auto it = g_plugins.find(key);
+    if (it != g_plugins.end()) { *out = it->second; return true; }
+    if (R < 2 || R > VSR_MAX_R || V < 1 || V > VSR_MAX_V || K < 1 || K > 15) {
+        why = "outside the packed encoding's range (ReplicaCount 2..7, |Values| 1..7, StartViewOnTimerLimit 0..14)";
+        return false;
+    }
+    const std::string dir = library_dir(), ldir = dir + "/layouts", src = dir + "/csrc/vsr_layout_plugin.cu";
+    const std::string name = "libvsr_layout_" + std::to_string(R) + "_" + std::to_string(V) + "_" + std::to_string(K) + ".so";
+    const std::string path = ldir + "/" + name;
+    time_t newest = 0; /* of the sources the plug-in is made of */
+    for (const char* f : {"vsr_layout_plugin.cu", "vsr_gpu_thunks.cuh", "vsr_gpu.cuh", "vsr_thunks.h", "vsr_actions.h", "vsr_layout.h",
+                          "vsr_flat_conv.h", "vsr_model.h"})
+        newest = std::max(newest, mtime_of(dir + "/csrc/" + f));
+    std::string open_why;
+    if (mtime_of(path) && mtime_of(path) >= newest && try_open_plugin(path, R, V, K, out, open_why)) {
+        g_plugins[key] = *out;
+        return true;
+    }
+    const char* jit = getenv("VSR_B200_JIT");
+    if (jit && jit[0] == '0') { why = "not built in, no usable " + path + (open_why.empty() ? "" : " (" + open_why + ")") + ", and VSR_B200_JIT=0"; return false; }
+    if (!mtime_of(src)) { why = "not built in, and the plug-in source " + src + " is not installed"; return false; }
+    mkdir(ldir.c_str(), 0755);
+    const std::string lock = path + ".lock";
+    const int fd = open(lock.c_str(), O_CREAT | O_RDWR, 0644);
+    if (fd >= 0) flock(fd, LOCK_EX);
+    bool ok = mtime_of(path) >= newest && mtime_of(path) && try_open_plugin(path, R, V, K, out, open_why); /* another rank was faster */
+    if (!ok) {
+        const char* nv = getenv("VSR_B200_NVCC");
+        std::string nvcc = nv ? nv : (access("/usr/local/cuda/bin/nvcc", X_OK) == 0 ? "/usr/local/cuda/bin/nvcc" : "nvcc");
+        const std::string tmp = path + ".tmp" + std::to_string((long)getpid()), log = path + ".log";
+        const std::string cmd = nvcc + " -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -diag-suppress 128"
+                                " -DVSR_ONLY_R=" + std::to_string(R) + " -DVSR_ONLY_V=" + std::to_string(V) + " -DVSR_ONLY_K=" + std::to_string(K) +
+                                " -shared -Xlinker -Bsymbolic -o '" + tmp + "' '" + src + "' > '" + log + "' 2>&1";
+        const int rc = system(cmd.c_str());
+        if (rc == 0 && rename(tmp.c_str(), path.c_str()) == 0) ok = try_open_plugin(path, R, V, K, out, open_why);
+        else {
+            unlink(tmp.c_str());
+            std::ifstream lf(log);
+            std::stringstream ss;
+            ss << lf.rdbuf();
+            std::string t = ss.str();
+            if (t.size() > 600) t = t.substr(0, 600) + " ...";
+            open_why = "compiling it failed (" + nvcc + ", log " + log + "): " + t;
+        }
+    }
+    if (fd >= 0) { flock(fd, LOCK_UN); close(fd); }
+    if (!ok) { why = "not built in, and " + open_why; return false; }
+    g_plugins[key] = *out;
+    return true;
 }
 
 /* ------------------------------------------------------------------ names */
@@ -352,12 +427,18 @@ static int bind_model(VsrModel* m, std::string& why) {
     if (I.start_view_on_timer_limit < 0) { why = "StartViewOnTimerLimit must be >= 0"; return VSR_RC_CONFIG_ERROR; }
     const int K = 1 + I.start_view_on_timer_limit;
     m->ops = find_model_ops(I.replica_count, I.value_count, K);
-    if (!m->ops) {
-        why = "no packed layout compiled for ReplicaCount=" + std::to_string(I.replica_count) + " |Values|=" + std::to_string(I.value_count) +
-              " StartViewOnTimerLimit=" + std::to_string(I.start_view_on_timer_limit) + " (add it to VSR_FOR_EACH_CONFIG in csrc/vsr_model.h)";
-        return VSR_RC_CONFIG_ERROR;
-    }
     m->gpu = find_gpu_ops(I.replica_count, I.value_count, K);
+    if (!m->ops) {
+        LayoutPlugin pl;
+        std::string pwhy;
+        if (!load_layout_plugin(I.replica_count, I.value_count, K, &pl, pwhy)) {
+            why = "packed layout for ReplicaCount=" + std::to_string(I.replica_count) + " |Values|=" + std::to_string(I.value_count) +
+                  " StartViewOnTimerLimit=" + std::to_string(I.start_view_on_timer_limit) + ": " + pwhy;
+            return VSR_RC_CONFIG_ERROR;
+        }
+        m->ops = pl.ops;
+        m->gpu = pl.gpu;
+    }
     if (I.value_count == 1) I.symmetry = 0; /* Permutations of a singleton: identity */
     m->run.symmetry = I.symmetry;
     m->run.use_view = I.view;
