@@ -99,7 +99,7 @@ def test_cfg_grammar(pkg):
     (lambda t: t.replace("    Nil = Nil\n", ""), "Nil"),
     (lambda t: t.replace("NEXT Next", "NEXT Foo"), "NEXT"),
     (lambda t: t.replace("AcknowledgedWriteNotLost", "NoSuchInvariant"), "NoSuchInvariant"),
-    (lambda t: t.replace("ReplicaCount = 3", "ReplicaCount = 6"), "no packed layout"),
+    (lambda t: t.replace("ReplicaCount = 3", "ReplicaCount = 8"), "outside the packed encoding's range"),
     (lambda t: t.replace("    StartViewOnTimerLimit = 2\n", ""), "StartViewOnTimerLimit"),
 ])
 def test_cfg_rejections_are_loud(pkg, mut, frag):
