@@ -37,6 +37,13 @@ def test_packed_next_equals_oracle_bfs_prefix(R, V, L, sym):
     assert out["checked"] == 8000 and out["mismatches"] == 0
 
 
+@pytest.mark.parametrize("R,V,L", [(2, 2, 1), (3, 1, 2), (3, 2, 1), (3, 3, 1), (4, 1, 1), (4, 2, 1), (5, 2, 1)])
+def test_every_other_builtin_layout_against_the_oracle(R, V, L):
+    """the built-in layouts (VSR_FOR_EACH_CONFIG) not named in the tests above: BFS prefix + random walks each"""
+    out = run_diff(R, V, L, 1 if V > 1 else 0, 4000, 1, 50000, 11)
+    assert out["checked"] == 4000 and out["mismatches"] == 0 and out["assumption_violations"] == 0
+
+
 @pytest.mark.parametrize("R,V,L,sym,seed", [(3, 2, 2, 1, 1), (3, 3, 3, 1, 2), (5, 2, 2, 1, 3), (3, 3, 3, 0, 4), (3, 2, 2, 0, 5), (5, 3, 2, 1, 6),
                                              (4, 3, 2, 1, 7)])
 def test_packed_next_equals_oracle_on_random_walks(R, V, L, sym, seed):
