@@ -1,4 +1,4 @@
-"""N>1 control flow of the fingerprint-sharded BFS (vsr-tlaplus_b200/dist.py) on CPU: world_size 2 and 4 over
+"""N>1 control flow of the fingerprint-sharded BFS (vsr-tlaplus_b200/dist.py) on CPU: world_size 2, 4 and 8 over
 gloo, with tests/host_engine.HostEngine standing in for the CUDA engine.  Checks ownership routing, the
 counts+records all-to-all, termination, G-independence of the result and the cross-rank trace walk."""
 import os
@@ -59,7 +59,7 @@ def run_world(world, cfg, port, **kw):
     return got
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_bfs_equals_oracle(world):
     cfg = (2, 2, 2, ("AcknowledgedWriteNotLost",))
     got = run_world(world, cfg, 29511 + world)
