@@ -1,0 +1,25 @@
+#!/bin/bash
+# Kernel experiments: build single-layout variants of libvsr_b200.so (seconds each) so ONE gpurun call can A/B them.
+#   tools/variants.sh                       builds build/variants/libvsr_b200_<name>.so for the variants below (cfg2 layout)
+#   tools/variants.sh R V K                 same for another layout
+# On the GPU box:  for v in build/variants/*.so; do VSR_B200_LIB=$v python tools/quick.py 3 2 2 0 0; done
+# Each variant is the default kernel plus -D flags (see "#ifdef VSR_EXP_" in csrc/vsr_gpu.cuh); "base" has none.
+set -e
+R=${1:-3}; V=${2:-2}; K=${3:-3}
+cd "$(dirname "$0")/../vsr-tlaplus_b200/csrc"
+OUT=../../build/variants; mkdir -p $OUT
+ARCH="-gencode arch=compute_100a,code=sm_100a"
+ONLY="-DVSR_ONLY_R=$R -DVSR_ONLY_V=$V -DVSR_ONLY_K=$K"
+g++ -O2 -std=c++17 -fPIC $ONLY -c vsr_host.cpp -o $OUT/vsr_host.o
+build() { # name, flags
+    nvcc $ARCH -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -diag-suppress 128 $ONLY $2 -c vsr_gpu.cu -o $OUT/vsr_gpu_$1.o
+    nvcc $ARCH -shared -Xlinker -Bsymbolic -o $OUT/libvsr_b200_$1.so $OUT/vsr_gpu_$1.o $OUT/vsr_host.o -ldl
+    rm -f $OUT/vsr_gpu_$1.o
+    echo "built $OUT/libvsr_b200_$1.so"
+}
+build base ""
+build emit_uv "-DVSR_EXP_EMIT_UV"
+build home_lowbits "-DVSR_EXP_HOME_LOWBITS"
+build prefetch "-DVSR_EXP_PREFETCH"
+build all3 "-DVSR_EXP_EMIT_UV -DVSR_EXP_HOME_LOWBITS -DVSR_EXP_PREFETCH"
+rm -f $OUT/vsr_host.o

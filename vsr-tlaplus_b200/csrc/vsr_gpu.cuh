@@ -149,7 +149,13 @@ __device__ __forceinline__ uint64_t make_meta(int level, uint32_t auxkey, uint32
 
 /* lock-free insert-if-absent; linear probing over 16-byte entries.  (e0, e1) is the entry at the home slot, loaded by the
    caller as early as the fingerprint was known so that the HBM round trip overlaps the rest of the successor's work. */
-__device__ __forceinline__ unsigned long long table_home(unsigned long long mask, uint64_t fp) { return mix64(fp) & mask; }
+__device__ __forceinline__ unsigned long long table_home(unsigned long long mask, uint64_t fp) {
+#ifdef VSR_EXP_HOME_LOWBITS /* experiment (tools/variants.sh): the Rabin fingerprint's own low bits, no second mix */
+    return fp & mask;
+#else
+    return mix64(fp) & mask;
+#endif
+}
 __device__ __forceinline__ int table_insert_from(uint64_t* table, unsigned long long mask, unsigned long long h, uint64_t e0, uint64_t e1,
                                                  uint64_t fp, uint64_t meta, unsigned& probes, unsigned& collisions) {
     for (unsigned tries = 0;; tries++) {
@@ -297,6 +303,9 @@ template <class L> struct Expander {
 
     /* returns this lane's counts for the run's statistics: successors generated (low half) | seen-set probes (high half);
        the caller keeps the running sums in registers (a warp reduction per batch cost 25 shuffles) */
+#ifdef VSR_EXP_EMIT_UV /* experiment: VIEW on/off decided at the call, one copy of the hash code on the hot path */
+    template <bool UV>
+#endif
     static __device__ __noinline__ unsigned long long emit(const ExpandParams& P, Smem& B, WarpStage<L>& S, int lane, const Row n, int mult,
                                                            int cand, int si, bool act) {
         unsigned gen = 0, probes = 0, coll = 0;
@@ -317,14 +326,22 @@ template <class L> struct Expander {
             if (mult < 0) {
                 atomicCAS(&P.ctr->error, 0, mult);
             } else if (mult > 0) {
+#ifdef VSR_EXP_EMIT_UV
+                uint64_t fp = fp64_view8_t<L, UV>(B.fp_tab, v);
+#else
                 uint64_t fp = fp64_view8<L>(B.fp_tab, v, P.run.use_view != 0);
+#endif
                 if (fp == 0) fp = 1;
                 const int owner = P.world > 1 ? (int)(fp >> P.owner_shift) : P.rank;
                 /* start the seen-set probe now; the check hash, aux key and tags are computed under its latency */
                 const unsigned long long home = table_home(P.table_mask, fp);
                 ulonglong2 first = make_ulonglong2(0, 0);
                 if (owner == P.rank) first = __ldcg(reinterpret_cast<const ulonglong2*>(P.table + 2 * home));
+#ifdef VSR_EXP_EMIT_UV
+                const uint32_t chk = check_hash_t<L, UV>(v);
+#else
                 const uint32_t chk = check_hash<L>(v, P.run.use_view != 0);
+#endif
                 const uint32_t auxkey = O_::aux_key(v);
                 const uint64_t meta = make_meta(P.level, auxkey, chk);
                 const uint64_t parent_gid = make_gid(P.rank, P.in_base + B.round_first + si);
@@ -517,7 +534,11 @@ template <class L> struct Expander {
         const Row n = scratch(S, lane);
         int mult = 0;
         if (act) mult = O_::template step_grp<true, G>(P.run, parent, cand, n);
+#ifdef VSR_EXP_EMIT_UV
+        return P.run.use_view ? emit<true>(P, B, S, lane, n, mult, cand, si, act) : emit<false>(P, B, S, lane, n, mult, cand, si, act);
+#else
         return emit(P, B, S, lane, n, mult, cand, si, act);
+#endif
     }
     /* one batch of <= 32 queued pairs of group G, pool[b .. b + k) */
     template <int G> static __device__ __forceinline__ unsigned long long batch(const ExpandParams& P, Smem& B, WarpStage<L>& S, int lane, int b,
@@ -621,7 +642,17 @@ template <class L> __global__ void __launch_bounds__(ExpandCfg<L>::WARPS * 32, 2
         __syncthreads();
         if (c >= nrounds) break;
         /* claim the round after this one now: the global atomic's latency hides under this round's work */
-        if (threadIdx.x == 0) next_round = atomicAdd(&P.ctr->work_next, 1ull);
+        if (threadIdx.x == 0) {
+            next_round = atomicAdd(&P.ctr->work_next, 1ull);
+#ifdef VSR_EXP_PREFETCH /* experiment: pull the next round's parents into L2 while this round runs */
+            const unsigned long long nx = next_round;
+            if (nx < nrounds) {
+                const unsigned long long nfirst = nx * Smem::NS;
+                const unsigned long long ncount = (P.n_in - nfirst) < (unsigned long long)Smem::NS ? (P.n_in - nfirst) : Smem::NS;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.in + nfirst * L::NW), "r"((uint32_t)(ncount * L::BYTES)) : "memory");
+            }
+#endif
+        }
         const unsigned long long first = c * Smem::NS;
         const int count = (int)((P.n_in - first) < (unsigned long long)Smem::NS ? (P.n_in - first) : Smem::NS);
         X.run_round(first, count);
