@@ -10,11 +10,11 @@ cd "$(dirname "$0")/../vsr-tlaplus_b200/csrc"
 OUT=../../build/variants; mkdir -p $OUT
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 ONLY="-DVSR_ONLY_R=$R -DVSR_ONLY_V=$V -DVSR_ONLY_K=$K"
-g++ -O2 -std=c++17 -fPIC $ONLY -c vsr_host.cpp -o $OUT/vsr_host.o
 build() { # name, flags
+    g++ -O2 -std=c++17 -fPIC $ONLY $2 -c vsr_host.cpp -o $OUT/vsr_host_$1.o   # the host side shares the flags (fingerprints must agree)
     nvcc $ARCH -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -diag-suppress 128 $ONLY $2 -c vsr_gpu.cu -o $OUT/vsr_gpu_$1.o
-    nvcc $ARCH -shared -Xlinker -Bsymbolic -o $OUT/libvsr_b200_$1.so $OUT/vsr_gpu_$1.o $OUT/vsr_host.o -ldl
-    rm -f $OUT/vsr_gpu_$1.o
+    nvcc $ARCH -shared -Xlinker -Bsymbolic -o $OUT/libvsr_b200_$1.so $OUT/vsr_gpu_$1.o $OUT/vsr_host_$1.o -ldl
+    rm -f $OUT/vsr_gpu_$1.o $OUT/vsr_host_$1.o
     echo "built $OUT/libvsr_b200_$1.so"
 }
 build base ""
@@ -22,4 +22,4 @@ build emit_uv "-DVSR_EXP_EMIT_UV"
 build home_lowbits "-DVSR_EXP_HOME_LOWBITS"
 build prefetch "-DVSR_EXP_PREFETCH"
 build all3 "-DVSR_EXP_EMIT_UV -DVSR_EXP_HOME_LOWBITS -DVSR_EXP_PREFETCH"
-rm -f $OUT/vsr_host.o
+build fasthash "-DVSR_EXP_FASTHASH"   # not TLC's fingerprint: measures what FP64 costs, nothing else

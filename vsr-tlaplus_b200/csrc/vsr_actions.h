@@ -712,6 +712,28 @@ inline void fp64_build_slices(uint64_t s8[8 * 256]) {
 
 template <class L, bool USE_VIEW, class W> VSR_HD uint64_t fp64_view8_t(const uint64_t* __restrict__ s8, const W& w) {
     static_assert(L::NW % 2 == 0, "whole 64-bit words");
+#ifdef VSR_EXP_FASTHASH
+    /* experiment only (tools/variants.sh): what the 48-lookup FP64 walk costs.  A multiply-xorshift hash of the same
+       words; NOT TLC's fingerprint function, so never the default. */
+    {
+        constexpr int full_ = L::VIEW_BITS >> 5, rem_ = L::VIEW_BITS & 31;
+        constexpr int nw_ = USE_VIEW ? (full_ + (rem_ ? 1 : 0)) : L::NW;
+        uint64_t h = FP64_POLY;
+        VSR_UNROLL
+        for (int i = 0; i < nw_; i += 2) {
+            uint32_t lo = rdw(w, i), hi = i + 1 < nw_ ? rdw(w, i + 1) : 0u;
+            if (USE_VIEW && i == full_) lo &= (1u << rem_) - 1u;
+            if (USE_VIEW && i + 1 == full_) hi &= (1u << rem_) - 1u;
+            h ^= ((uint64_t)hi << 32) | lo;
+            h *= 0x9E3779B97F4A7C15ULL;
+            h ^= h >> 29;
+        }
+        h *= 0xBF58476D1CE4E5B9ULL;
+        h ^= h >> 32;
+        (void)s8;
+        return h;
+    }
+#endif
     uint64_t fp = FP64_POLY;
     constexpr int full = L::VIEW_BITS >> 5, rem = L::VIEW_BITS & 31;
     /* bytes of whole zero words after the VIEW prefix are not hashed by the byte form either: hash ceil(nw/2) pairs,
