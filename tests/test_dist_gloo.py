@@ -24,10 +24,19 @@ def _worker(rank, world, port, cfg, q, kw):
     from host_engine import HostEngine
     R, V, L, inv = cfg
     mc = pkg.ModelChecker.from_constants(R, V, L, invariants=inv)
-    eng = HostEngine(mc, rank, world)
     part = kw.pop("part_states", 0)
+    if kw.pop("engine", "host") == "gpu":  # every rank on cuda:0: the kernels' world > 1 paths on a one-GPU box
+        eng = vdist.GpuEngine(mc, rank, world, device=0, table_capacity=1 << 21, frontier_capacity=1 << 19, send_capacity=1 << 19,
+                              collect_levels=True)
+    else:
+        eng = HostEngine(mc, rank, world)
     res = vdist.ShardedBfs(eng, rank, world, part_states=part).run(**kw)
-    levels = [sorted(lv) for lv in eng.levels if lv or True]
+    if hasattr(eng, "levels"):
+        levels = [sorted(lv) for lv in eng.levels if lv or True]
+    else:
+        sb = mc.state_bytes
+        raws = [eng.collected(d + 1) for d in range(res.depth)]
+        levels = [sorted(raw[i:i + sb] for i in range(0, len(raw), sb)) for raw in raws]
     trace = vdist.replay_trace(mc, res.trace_cands) if (res.trace_cands or res.rc == 12) and rank == 0 else []
     q.put((rank, dict(rc=res.rc, generated=res.generated, distinct=res.distinct, depth=res.depth, complete=res.complete,
                       level_sizes=res.level_sizes, level_generated=res.level_generated, queue=res.queue,
@@ -42,16 +51,18 @@ def run_world(world, cfg, port, **kw):
     for p in procs:
         p.start()
     import queue as _queue
+    import time as _time
     got = []
+    deadline = _time.time() + 420  # a stuck rendezvous or collective must not hang the suite
     while len(got) < world:
         try:
             got.append(q.get(timeout=2))
         except _queue.Empty:
             dead = [p for p in procs if p.exitcode not in (None, 0)]
-            if dead:
+            if dead or _time.time() > deadline:
                 for p in procs:
                     p.kill()
-                raise AssertionError("a rank died (exit code %s)" % dead[0].exitcode)
+                raise AssertionError("a rank died (exit code %s)" % dead[0].exitcode if dead else "ranks still running after 420 s")
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -117,3 +128,25 @@ def test_sharded_bfs_in_sub_wavefronts():
         assert res["rc"] == 0 and res["complete"]
         assert (res["generated"], res["distinct"], res["depth"]) == (o.generated, o.distinct, o.depth)
         assert res["level_sizes"] == o.level_sizes
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: first run is at round end")
+@pytest.mark.parametrize("world,part", [(2, 0), (4, 0), (2, 5000)])
+def test_ranks_sharing_one_gpu_match_oracle(world, part):
+    """The CUDA engine's world > 1 paths (send buffers, sender-side duplicate filter, insert_kernel, ownership by
+    fingerprint bits) on a box with ONE GPU: `world` processes all on cuda:0, records exchanged over gloo through host
+    memory.  cfg2 to depth 12 against the oracle: scalars, level sizes, and the shards partition every level."""
+    cfg = (3, 2, 2, ("AcknowledgedWriteNotLost",))
+    got = run_world(world, cfg, 29560 + world + (7 if part else 0), engine="gpu", part_states=part, max_depth=12, stop_on_violation=False,
+                    want_trace=False)
+    o = orc.bfs(orc.params(3, 2, 2), workers=8, max_depth=12, keep_trace=False)
+    for rank, res, levels, _ in got:
+        assert res["rc"] == 0
+        assert (res["generated"], res["distinct"], res["depth"]) == (o.generated, o.distinct, o.depth)
+        assert res["level_sizes"] == o.level_sizes
+        assert res["level_generated"] == o.level_generated
+    for d in range(got[0][1]["depth"]):
+        parts = [set(levels[d]) for _, _, levels, _ in got]
+        assert sum(len(p) for p in parts) == len(set().union(*parts)) == o.level_sizes[d]
+    assert sum(r["sent"] for _, r, _, _ in got) > 0

@@ -149,13 +149,15 @@ class ShardedBfs:
     def __init__(self, engine, rank: int, world: int, group=None, part_states: int = 0):
         self.e, self.rank, self.world, self.group = engine, rank, world, group
         self.part_states = part_states  # frontier states per sub-wavefront and rank (0 = whole level at once)
+        # NCCL moves device tensors; gloo (CPU tests, and ranks that share one GPU in a test) gets host tensors
+        self._nccl = world > 1 and dist.get_backend(group) == "nccl"
+        self._cdev = getattr(engine, "dev", torch.device("cpu")) if self._nccl else torch.device("cpu")
 
     # -- collectives (no-ops when world == 1) ---------------------------------------------------
     def _allreduce(self, vals: List[int], op) -> List[int]:
         if self.world == 1:
             return list(vals)
-        dev = getattr(self.e, "dev", torch.device("cpu"))
-        t = torch.tensor(vals, dtype=torch.int64, device=dev)
+        t = torch.tensor(vals, dtype=torch.int64, device=self._cdev)
         dist.all_reduce(t, op=op, group=self.group)
         return [int(x) for x in t.cpu().tolist()]
 
@@ -163,7 +165,7 @@ class ShardedBfs:
         """counts all-to-all, then the records; returns the number of records this rank sent"""
         if self.world == 1:
             return 0
-        counts = self.e.send_counts()  # int64[world] on the engine's device
+        counts = self.e.send_counts().to(self._cdev)  # int64[world]
         if int(counts.max()) > self.e.send_capacity:
             raise ck.VsrError(152, f"send buffer overflow: {int(counts.max())} records for one destination, capacity "
                                    f"{self.e.send_capacity}")
@@ -176,7 +178,7 @@ class ShardedBfs:
         rb = self.e.record_bytes
         parts = [self.e.send_slice(p, sc[p]) for p in range(self.world)]
         out = recv.reshape(-1)[: total * rb]
-        if dist.get_backend(self.group) == "nccl":
+        if self._nccl:
             # grouped ncclSend/ncclRecv straight out of the per-destination send buffers over NVLink: no staging copy;
             # pairs with nothing to move are skipped on both sides (both know the counts)
             ops, off = [], 0
@@ -191,9 +193,12 @@ class ShardedBfs:
                     w.wait()
         else:
             # gloo (CPU tests) has no list all-to-all: one variable-size all_to_all_single over a concatenation
-            inp = torch.cat(parts) if sum(sc) else parts[0][:0]
-            dist.all_to_all_single(out, inp, output_split_sizes=[c * rb for c in rcnt], input_split_sizes=[c * rb for c in sc],
+            inp = (torch.cat(parts) if sum(sc) else parts[0][:0]).to(self._cdev)
+            hout = out if out.device == self._cdev else torch.empty(total * rb, dtype=torch.uint8)
+            dist.all_to_all_single(hout, inp, output_split_sizes=[c * rb for c in rcnt], input_split_sizes=[c * rb for c in sc],
                                    group=self.group)
+            if hout is not out:
+                out.copy_(hout)
         self.e.insert(recv, total)
         return sum(sc)
 
@@ -274,10 +279,9 @@ class ShardedBfs:
     def _walk_trace(self, gid: int) -> List[int]:
         """follow (parent, candidate) records across ranks from a state back to Init"""
         cands: List[int] = []
-        dev = getattr(self.e, "dev", torch.device("cpu"))
         for _ in range(4096):
             owner = gid >> GID_SHIFT
-            buf = torch.zeros(2, dtype=torch.int64, device=dev)
+            buf = torch.zeros(2, dtype=torch.int64, device=self._cdev)
             if owner == self.rank:
                 parent, cand = self.e.trace_record(gid & ((1 << GID_SHIFT) - 1))
                 buf[0], buf[1] = parent, cand
