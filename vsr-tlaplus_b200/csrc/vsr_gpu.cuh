@@ -200,7 +200,11 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_
 /* ------------------------------------------------------------------ expand kernel */
 
 constexpr int SCAP = 64;      /* staged new states per warp */
+#ifdef VSR_QPS
+constexpr int QPS = VSR_QPS;  /* tools/variants.sh "qps1": a pool so small that the overflow path (leftovers) runs all the time */
+#else
 constexpr int QPS = 10;       /* pool entries per parent state (pool = QPS * states per block round) */
+#endif
 
 template <class L> struct WarpStage {
     alignas(16) uint32_t stage[SCAP * L::NW];    /* new states, packed back to back for the bulk store */
