@@ -10,8 +10,16 @@
  * golden vector the reference holds is state_transfer_violation_trace.txt (24 states): this oracle
  * is pinned to it (every transition replays through Next below, the final state violates
  * AcknowledgedWriteNotLost, and print_state() reproduces the file's text byte for byte apart from
- * `location` strings and three variables the file predates).  State counts, fingerprints and BFS
- * depth are "parity unpinned": no file in the reference records them.
+ * `location` strings and three variables the file predates).
+ * Second pin: the reference's own SOURCE TEXT.  oracle/tla_eval.py parses VSR.tla as it lies under
+ * /root/reference and enumerates Init/Next the way TLC does; tests/test_spec_text.py compares it with
+ * this file — complete state spaces level by level (cfg1 = BASELINE configs[0]: 76 distinct / 100
+ * generated / depth 14, and two neighbours), successor sets state by state along the golden trace,
+ * random walks on cfg2/cfg3/cfg4 constants, the recovery actions with RestartEmptyLimit 1 and 2, both
+ * safety invariants, orbit counts under SYMMETRY: 0 differences (tests/golden/spec_text_results.json).
+ * Still "parity unpinned": TLC's FINGERPRINT values (its value serialisation and model-value intern
+ * order are TLC internals) and, for configurations too large for the text evaluator (cfg2's complete
+ * 1.17e9-state space, cfg3), the totals — there this oracle is the reference, with that caveat.
  *
  * Value model: records are C++ structs spelled out field by field, sets are ordered std::set,
  * the message bag is an ordered std::map record -> pending count — no bit packing, no slot
