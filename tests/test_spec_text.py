@@ -72,6 +72,12 @@ def test_successors_along_the_golden_trace_and_around_it(pkg):
     fx = json.load(open(os.path.join(ROOT, "tests", "golden", "state_transfer_trace.json")))
     P = S.Pair(pkg, 3, 3, 3)
     flats = [P.Flat.from_buffer_copy(zlib.decompress(base64.b64decode(s["flat_zlib_b64"]))) for s in fx["states"]]
+    # the published trace is a behaviour of the CURRENT text: each recorded state is a successor of the one before, under
+    # the recorded action name (the file predates three variables; they sit at their Init values)
+    pys = [S.to_py(P.q, f) for f in flats]
+    for i in range(len(pys) - 1):
+        succ = P.ev.successors(pys[i])
+        assert any(a == fx["states"][i + 1]["action"] and sp == pys[i + 1] for a, sp in succ), (i + 2, fx["states"][i + 1]["action"])
     rng = random.Random(7)
     n = 0
     for f in flats:
