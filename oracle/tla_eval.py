@@ -1078,14 +1078,17 @@ def bfs(ev, view="view", invariant=None, max_depth=0, max_states=0):
             seen.add(k)
             frontier.append(st)
     out = dict(level_sizes=[len(frontier)], level_generated=[], generated=len(init), distinct=len(frontier), depth=1, violation_depth=0,
-               levels=[list(frontier)], ambiguous_choose=0)
+               levels=[list(frontier)], ambiguous_choose=0, deadlock_depth=0)
     if invariant and any(not ev.holds(invariant, st) for st in frontier):
         out["violation_depth"] = 1
     while frontier and not (max_depth and out["depth"] >= max_depth) and not (max_states and out["distinct"] >= max_states):
         nxt, gen = [], 0
         for st in frontier:
             ev.choose_log = []
-            for _, sp in ev.successors(st):
+            succ = ev.successors(st)
+            if not succ and not out["deadlock_depth"]:
+                out["deadlock_depth"] = out["depth"]  # TLC's "deadlock": a state Next cannot leave
+            for _, sp in succ:
                 gen += 1
                 k = ev.project(sp, view) if view else Fn(dict(sp))
                 if k not in seen:

@@ -29,6 +29,10 @@ def test_whole_state_space_from_the_spec_text(pkg, R, V, L, expect):
     assert (r["distinct"], r["generated"], r["depth"]) == expect == (o.distinct, o.generated, o.depth)
     assert r["level_sizes"] == o.level_sizes and r["level_generated"] == o.level_generated
     assert r["violation_depth"] == 0 and o.rc == 0
+    # TLC checks deadlock unless told not to; the text has terminal states (every message delivered, every value used, timer
+    # budget spent), so "full BFS" presupposes -deadlock.  Both sides agree that they exist.
+    assert r["deadlock_depth"] > 0
+    assert orc.bfs(orc.params(R, V, L, symmetry=False), workers=1, check_deadlock=True, keep_trace=False).rc == 11
 
 
 @needs_reference
@@ -132,6 +136,66 @@ def test_cfg2_counterexample_is_a_behaviour_of_the_spec_text(pkg):
     path = S.find_behaviour(ev, acts[1:], "AcknowledgedWriteNotLost")
     assert path is not None and len(path) == 28
     assert ev.holds("AcknowledgedWriteNotLost", path[-2]) and not ev.holds("AcknowledgedWriteNotLost", path[-1])
+
+
+@needs_reference
+@pytest.mark.parametrize("R,V,L,walks,steps", [(3, 2, 2, 5, 40), (3, 3, 3, 3, 40), (2, 3, 2, 3, 30)])
+def test_product_host_next_against_the_text_directly(pkg, R, V, L, walks, steps):
+    """No oracle in between: the PRODUCT's packed successor function (vsr_successors: canonical value labels, one successor
+    standing for `mult` bindings under SYMMETRY) against the text, orbit by orbit.  Both sides are reduced to the smallest
+    relabelling of the whole state (aux variables included) under Permutations(Values)."""
+    import collections
+    import itertools
+    import spec_text as S
+    T = S.T
+    ev = S.evaluator(R, V, L)
+    mc = pkg.ModelChecker.from_constants(R, V, L)  # SYMMETRY on
+    vals = sorted(ev.c["Values"], key=lambda m: m.name)
+    perms = [dict(zip(vals, p)) for p in itertools.permutations(vals)]
+
+    def relabel(v, pi):
+        if isinstance(v, T.ModelValue):
+            return pi.get(v, v)
+        if isinstance(v, frozenset):
+            return frozenset(relabel(x, pi) for x in v)
+        if isinstance(v, T.Fn):
+            return T.Fn({relabel(k, pi): relabel(x, pi) for k, x in v.d.items()})
+        return v
+
+    def orbit(st):
+        f = T.Fn(dict(st))
+        return min((relabel(f, pi) for pi in perms), key=T.vkey)
+    rng = random.Random(R + 10 * V + 100 * L)
+    compared = 0
+    for _ in range(walks):
+        state = mc.init_state()
+        for _ in range(steps):
+            py = T.parse_state_record(mc.to_tla(state))
+            want = collections.Counter((a, orbit(sp)) for a, sp in ev.successors(py))
+            got = collections.Counter()
+            succ = mc.successors(state)
+            for sb, act, mult in succ:
+                got[(S.ACTIONS[act], orbit(T.parse_state_record(mc.to_tla(sb))))] += mult
+            assert got == want, {k: T.fmt(v) for k, v in py.items()}
+            compared += 1
+            if not succ:
+                break
+            state = rng.choice(succ)[0]
+    assert compared >= walks * steps // 2
+
+
+@needs_reference
+def test_two_clients_abort_in_the_text_as_the_loader_says(pkg):
+    """ClientCount = 2 is refused by the loader with "TLC aborts on m.commit" (VSR.tla:421): executing the text confirms
+    it — the first ReceivePrepareMsg evaluates the non-existent record field"""
+    import spec_text as S
+    ev = S.T.load_vsr(S.SPEC, 3, 2, ["v1"], 1)
+    frontier = ev.initial_states()
+    with pytest.raises(S.T.EvalError, match="has no field commit"):
+        for _ in range(4):
+            frontier = [sp for st in frontier for _, sp in ev.successors(st)][:300]
+    with pytest.raises(pkg.VsrError, match="m.commit"):
+        pkg.ModelChecker.from_cfg_text(pkg.cfg_text(3, ["v1"], 1).replace("ClientCount = 1", "ClientCount = 2"))
 
 
 def test_oracle_equals_the_committed_spec_text_results():
