@@ -12,7 +12,8 @@ vsr-revisited/paper/VSR.tla (read from /root/reference — this script only runs
 tests/test_spec_text.py::test_oracle_equals_the_committed_spec_text_results checks the oracle against `state_spaces`
 on every machine (the GPU box has no /root/reference).
 
-    python tests/golden/make_spec_text_fixture.py
+    python tests/golden/make_spec_text_fixture.py                          # everything (about 20 minutes)
+    python tests/golden/make_spec_text_fixture.py --add-space R V L DEPTH  # one more state space (DEPTH 0 = complete)
 """
 import base64
 import json
@@ -31,17 +32,31 @@ import _pkg  # noqa: E402
 import spec_text as S  # noqa: E402
 
 
+def space_row(R, V, L, depth):
+    t = time.time()
+    r = S.T.bfs(S.evaluator(R, V, L), invariant="AcknowledgedWriteNotLost", max_depth=depth)
+    row = dict(R=R, V=V, L=L, max_depth=depth, complete=depth == 0, level_sizes=r["level_sizes"], level_generated=r["level_generated"],
+               distinct=r["distinct"], generated=r["generated"], depth=r["depth"], violation_depth=r["violation_depth"],
+               states_with_an_ambiguous_choose=r["ambiguous_choose"], seconds=round(time.time() - t, 1))
+    if depth:  # the last level reached is not expanded by a depth-bounded run of the oracle: keep what both sides define
+        row["level_generated"] = r["level_generated"][:len(r["level_sizes"]) - 1]
+    return row
+
+
 def main():
     pkg = _pkg.load()
+    if len(sys.argv) == 6 and sys.argv[1] == "--add-space":  # one more state space into the existing file (long runs)
+        R, V, L, depth = map(int, sys.argv[2:6])
+        row = space_row(R, V, L, depth)
+        path = os.path.join(HERE, "spec_text_results.json")
+        out = json.load(open(path))
+        out["state_spaces"] = [x for x in out["state_spaces"] if (x["R"], x["V"], x["L"]) != (R, V, L)] + [row]
+        json.dump(out, open(path, "w"), indent=1)
+        print("added", R, V, L, row["distinct"], row["generated"], row["depth"], row["seconds"], "s")
+        return
     out = {"source": "vsr-revisited/paper/VSR.tla (Vanlightly/vsr-tlaplus), executed by oracle/tla_eval.py", "state_spaces": []}
     for R, V, L, depth in [(2, 1, 1, 0), (2, 2, 1, 0), (2, 2, 2, 0), (3, 1, 1, 0), (2, 3, 2, 0), (2, 2, 3, 0), (3, 2, 1, 9), (3, 2, 2, 8), (3, 3, 3, 7), (5, 2, 2, 6)]:
-        t = time.time()
-        r = S.T.bfs(S.evaluator(R, V, L), invariant="AcknowledgedWriteNotLost", max_depth=depth)
-        row = dict(R=R, V=V, L=L, max_depth=depth, complete=depth == 0, level_sizes=r["level_sizes"], level_generated=r["level_generated"],
-                   distinct=r["distinct"], generated=r["generated"], depth=r["depth"], violation_depth=r["violation_depth"],
-                   states_with_an_ambiguous_choose=r["ambiguous_choose"], seconds=round(time.time() - t, 1))
-        if depth:  # the last level reached is not expanded by a depth-bounded run of the oracle: keep what both sides define
-            row["level_generated"] = r["level_generated"][:len(r["level_sizes"]) - 1]
+        row = space_row(R, V, L, depth)
         out["state_spaces"].append(row)
         print(row["R"], row["V"], row["L"], row["distinct"], row["generated"], row["depth"], row["seconds"], "s", flush=True)
 

@@ -139,6 +139,18 @@ def test_cfg2_counterexample_is_a_behaviour_of_the_spec_text(pkg):
 
 
 @needs_reference
+def test_cfg3_counterexample_of_the_gpu_run_is_a_behaviour_of_the_spec_text(pkg):
+    """README constants on 4 GPUs (profiles/cfg3_counterexample): violation at depth 24, the length of the published trace;
+    a behaviour of the text with the GPU run's action names exists and ends with v1 acknowledged and every log empty"""
+    import spec_text as S
+    acts = json.load(open(os.path.join(ROOT, "profiles", "cfg3_counterexample", "counterexample_actions.json")))["actions"]
+    ev = S.evaluator(3, 3, 3)
+    path = S.find_behaviour(ev, acts[1:], "AcknowledgedWriteNotLost")
+    assert path is not None and len(path) == 24
+    assert all(ev.holds("AcknowledgedWriteNotLost", st) for st in path[:-1]) and not ev.holds("AcknowledgedWriteNotLost", path[-1])
+
+
+@needs_reference
 @pytest.mark.parametrize("R,V,L,walks,steps", [(3, 2, 2, 5, 40), (3, 3, 3, 3, 40), (2, 3, 2, 3, 30)])
 def test_product_host_next_against_the_text_directly(pkg, R, V, L, walks, steps):
     """No oracle in between: the PRODUCT's packed successor function (vsr_successors: canonical value labels, one successor
