@@ -233,8 +233,6 @@ class Parser:
         while not self.blocked():
             tok = self.peek()
             if tok.kind == "op" and tok.text in BINOPS and BINOPS[tok.text] >= minp:
-                if tok.text in ("/\\", "\\/") and False:
-                    pass
                 self.next()
                 right = self.expr(BINOPS[tok.text] + 1)
                 left = ("bin", tok.text, left, right)
@@ -572,9 +570,8 @@ class Evaluator:
             else:
                 params, body = self.m.body(name)
                 clo = Closure(params, body, {})
-            vals = [a if isinstance(a, Closure) else a for a in args]
             e2 = dict(clo.env)
-            e2.update(zip(clo.params, vals))
+            e2.update(zip(clo.params, args))
             return self.ev(clo.body, e2)
         if f:
             return f(self, *args)
@@ -1035,23 +1032,26 @@ BUILTINS = {
 # ------------------------------------------------------------------------------------------------ convenience
 
 
-def parse_state_record(text, model_values=()):
-    """a state printed as `var |-> value, ...` lines (the oracle's printer; TLC's dumpTrace records) -> dict"""
-    e = parse_expression("[" + text.strip().rstrip(",") + "]")
-    ev = Evaluator.__new__(Evaluator)
-    ev.m = type("M", (), {"defs": {}, "variables": []})()
-    ev.c = {}
-    ev.varset = set()
-    ev.s, ev.sp, ev.choose_log, ev.choose_pick, ev._primed = {}, None, [], 0, {}
+class _NoModule:
+    defs, variables, constants = {}, [], []
 
-    class MV(dict):
-        def __missing__(self, k):
-            return ModelValue(k)
 
-        def __contains__(self, k):
-            return True
-    ev.c = MV()
-    return dict(ev.ev(e, {}).d)
+class _ModelValues(dict):
+    """constants of a printed value: every bare identifier is a model value (Normal, v1, PrepareMsg, Nil, ...)"""
+
+    def __missing__(self, k):
+        return ModelValue(k)
+
+    def __contains__(self, k):
+        return True
+
+
+def parse_state_record(text):
+    """a state printed as `var |-> value, ...` lines (the oracle's and the product's printers; TLC's dumpTrace records)
+    -> dict variable -> value"""
+    ev = Evaluator(_NoModule(), _ModelValues())
+    ev.c = _ModelValues()
+    return dict(ev.ev(parse_expression("[" + text.strip().rstrip(",") + "]"), {}).d)
 
 
 def load_vsr(path, R, C, values, L, restart=0):
