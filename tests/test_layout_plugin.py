@@ -24,6 +24,18 @@ def test_plugin_layout_matches_oracle_on_the_host(pkg):
         assert out["assumption_violations"] == 0
 
 
+def test_start_view_on_timer_limit_zero(pkg):
+    """StartViewOnTimerLimit = 0 (no timer-triggered view change: the view-change and state-transfer candidate groups are
+    EMPTY in the packed layout) is a legal constant; complete space (3 replicas, 2 values: 129 states without SYMMETRY)
+    and walks against the oracle"""
+    pkg.ModelChecker.from_constants(3, 2, 0)
+    exe = os.path.join(ROOT, "build", "diff_host")
+    for sym in (1, 0):
+        out = json.loads(subprocess.run([exe, "3", "2", "0", str(sym), "100000"], check=True, capture_output=True, text=True).stdout)
+        assert out["complete"] == 1 and out["mismatches"] == 0 and out["assumption_violations"] == 0, out
+    assert out["checked"] == 129
+
+
 def _load_in_subprocess(R, V, L, env):
     code = ("import sys; sys.path.insert(0, %r); import _pkg; pkg = _pkg.load()\n"
             "try:\n    pkg.ModelChecker.from_constants(%d, %d, %d); print('LOADED')\n"

@@ -496,7 +496,7 @@ template <class L> struct Ops {
     /* the enabled candidates of a state, in candidate order, through the register-mask form (host side of the C ABI's
        vsr_enabled_candidates, which cross-checks it against the one-candidate form) */
     template <int G> static VSR_HD int list_group(const RunCfg& run, const RegRow<L::NW>& st, uint32_t* out, int n) {
-        uint32_t m[grp_words(G)] = {};
+        uint32_t m[grp_words(G) > 0 ? grp_words(G) : 1] = {}; /* StartViewOnTimerLimit = 0 leaves the view-change groups empty */
         enabled_group<G>(run, st, m);
         for (int i = 0; i < grp_size(G); i++)
             if ((m[i >> 5] >> (i & 31)) & 1u) out[n++] = (uint32_t)(grp_begin(G) + i);
