@@ -53,7 +53,10 @@ typedef struct VsrModelInfo {
 /* ---- loading: TLC's `-config VSR.cfg VSR.tla` (grammar of vsr-revisited/paper/VSR.cfg:1-39).
  * tla_path may be NULL (the spec is hand-lowered; when given, it is verified to BE VSR.tla: module
  * name :1, the 20 VARIABLES :119-138, the 19 disjuncts of Next :896-918).  On failure returns
- * 150/151 and writes a message to err. */
+ * 150/151 and writes a message to err.
+ * Constants: ReplicaCount 2..7, |Values| 1..7, StartViewOnTimerLimit 0..14, ClientCount 1, RestartEmptyLimit 0.  The
+ * packed layouts of the reference's configurations and their neighbours are built in; any other combination is
+ * compiled on first use into <library dir>/layouts/ (needs nvcc; VSR_B200_JIT=0 turns that into a 151). */
 int vsr_load(const char* cfg_path, const char* tla_path, VsrModel** out, char* err, size_t errcap);
 /* same, from the text of a cfg file */
 int vsr_load_cfg_text(const char* cfg_text, const char* tla_path, VsrModel** out, char* err, size_t errcap);
@@ -71,7 +74,9 @@ int vsr_init(const VsrModel* m, void* state_out);                        /* Init
  * action_ids[i] = VSR_ACT_*, mult[i] = TLC bindings that successor stands for; returns the number
  * of successors, or a negative E_* code if one cannot be represented. */
 int vsr_successors(const VsrModel* m, const void* state, void* out, size_t cap, uint8_t* action_ids, uint32_t* mult);
-/* candidate (action, binding) indices whose guard holds in `state`, in the order vsr_successors emits them */
+/* candidate (action, binding) indices whose guard holds in `state`, in the order vsr_successors emits them.  Evaluates the
+ * guards in both of their forms (one candidate at a time, and the register-mask form of the GPU scan); -100 if they
+ * ever disagree */
 int vsr_enabled_candidates(const VsrModel* m, const void* state, uint32_t* out, size_t cap);
 int vsr_canon(const VsrModel* m, void* state);                           /* SYMMETRY representative, VSR.tla:151 */
 uint64_t vsr_fingerprint(const VsrModel* m, const void* state);          /* FP64 of the VIEW projection, VSR.tla:149-150 */
