@@ -90,6 +90,18 @@ def test_cfg_grammar(pkg):
     assert pkg.ModelChecker.from_cfg_text(pkg.cfg_text(2, ["v1"], 1)).info.symmetry == 0
 
 
+def test_specification_spec_is_init_next(pkg):
+    """VSR.cfg's first line is a commented-out SPECIFICATION; `SPECIFICATION Spec` (VSR.tla:966: Init /\\ [][Next]_vars /\\
+    WF_vars(Next)) in place of INIT/NEXT checks the same invariants over the same state graph, as in TLC"""
+    base = pkg.cfg_text(3, ["v1", "v2"], 2)
+    spec = base.replace("INIT Init\n", "").replace("NEXT Next\n", "SPECIFICATION Spec\n")
+    assert "SPECIFICATION Spec" in spec and "INIT" not in spec
+    a, b = pkg.ModelChecker.from_cfg_text(base), pkg.ModelChecker.from_cfg_text(spec)
+    assert a.successors(a.init_state()) == b.successors(b.init_state())
+    with pytest.raises(pkg.VsrError, match="Spec"):
+        pkg.ModelChecker.from_cfg_text(spec.replace("SPECIFICATION Spec", "SPECIFICATION LivenessSpec"))
+
+
 @pytest.mark.parametrize("mut,frag", [
     (lambda t: t.replace("INIT Init", "SPECIFICATION Spec\nINIT Init"), "SPECIFICATION"),
     (lambda t: t + "PROPERTY ViewChangeCompletes\n", "PROPERTY"),

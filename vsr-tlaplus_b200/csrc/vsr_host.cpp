@@ -325,7 +325,7 @@ static int parse_cfg(const std::string& text, VsrModel* m, std::string& why) {
     std::map<std::string, std::string> mvs;
     std::vector<std::string> values;
     bool have_values = false;
-    std::string init, next, view, symm;
+    std::string init, next, view, symm, spec;
     std::vector<std::string> invs;
     m->check_deadlock_cfg = -1;
     auto at = [&](size_t i) -> std::string { return i < t.size() ? t[i].s : std::string(); };
@@ -369,9 +369,14 @@ static int parse_cfg(const std::string& text, VsrModel* m, std::string& why) {
         } else if (k == "CHECK_DEADLOCK") {
             m->check_deadlock_cfg = at(i + 1) == "TRUE" ? 1 : 0;
             i += 2;
-        } else if (k == "SPECIFICATION" || k == "PROPERTY" || k == "PROPERTIES" || k == "CONSTRAINT" || k == "CONSTRAINTS" ||
+        } else if (k == "SPECIFICATION") {
+            /* Spec == Init /\ [][Next]_vars /\ WF_vars(Next) (VSR.tla:966): for invariant checking TLC explores Init/Next
+               exactly as with INIT/NEXT; the fairness conjunct only matters to PROPERTY formulas, which are refused below */
+            spec = at(i + 1);
+            i += 2;
+        } else if (k == "PROPERTY" || k == "PROPERTIES" || k == "CONSTRAINT" || k == "CONSTRAINTS" ||
                    k == "ACTION_CONSTRAINT" || k == "ACTION_CONSTRAINTS" || k == "POSTCONDITION" || k == "ALIAS") {
-            why = "`" + k + "` is not supported: this checker runs INIT/NEXT safety checking of VSR.tla only (no temporal "
+            why = "`" + k + "` is not supported: this checker runs safety (invariant) checking of VSR.tla only (no temporal "
                   "formulas, liveness or constraints)" + where(i);
             return VSR_RC_CONFIG_ERROR;
         } else { why = "unexpected token `" + k + "`" + where(i); return VSR_RC_CONFIG_ERROR; }
@@ -386,6 +391,12 @@ static int parse_cfg(const std::string& text, VsrModel* m, std::string& why) {
     for (size_t a = 0; a < values.size(); a++)
         for (size_t b = a + 1; b < values.size(); b++)
             if (values[a] == values[b]) { why = "duplicate element `" + values[a] + "` in Values"; return VSR_RC_CONFIG_ERROR; }
+    if (!spec.empty()) {
+        if (!init.empty() || !next.empty()) { why = "the config names both SPECIFICATION and INIT/NEXT (TLC refuses that too)"; return VSR_RC_CONFIG_ERROR; }
+        if (spec != "Spec") { why = "SPECIFICATION `" + spec + "` unknown; VSR.tla defines `Spec` (:966)"; return VSR_RC_CONFIG_ERROR; }
+        init = "Init";
+        next = "Next";
+    }
     if (init != "Init") { why = "INIT must be `Init` (VSR.tla:323)"; return VSR_RC_CONFIG_ERROR; }
     if (next != "Next") { why = "NEXT must be `Next` (VSR.tla:896)"; return VSR_RC_CONFIG_ERROR; }
     if (!view.empty() && view != "view") { why = "VIEW `" + view + "` unknown; VSR.tla defines `view` (:149)"; return VSR_RC_CONFIG_ERROR; }
