@@ -22,7 +22,8 @@ static void usage() {
             "  -depth N             stop after BFS depth N\n"
             "  -dumpTrace tlc FILE  write a counterexample in TLC's `dumpTrace tlc` format\n"
             "  -fp N                fingerprint polynomial index; only 0 (TLC's Polys[0]) is available\n"
-            "  -workers N           accepted for compatibility; the BFS runs on the GPU\n"
+            "  -workers N           accepted for compatibility; the BFS runs on the GPU (likewise -metadir, -checkpoint, -coverage,\n"
+            "                       -fpmem, -fpbits, -cleanup, -nowarning, -tool, ...); -recover and -dfid are refused\n"
             "  -gpu N               CUDA device ordinal (default 0)\n"
             "  -table N / -frontier N   seen-set slots / states per frontier buffer (default: from free memory)\n"
             "  -continue            keep exploring after the first violation\n"
@@ -51,8 +52,14 @@ int main(int argc, char** argv) {
             i += 2;
         } else if (a == "-fp" && i + 1 < argc) {
             if (atoi(argv[++i]) != 0) { fprintf(stderr, "Error: only -fp 0 is available\n"); return 255; }
-        } else if (a == "-workers" && i + 1 < argc) i++;
-        else if (a == "-gpu" && i + 1 < argc) o.device = atoi(argv[++i]);
+        } else if ((a == "-workers" || a == "-metadir" || a == "-checkpoint" || a == "-coverage" || a == "-userFile" || a == "-fpmem" ||
+                    a == "-fpbits" || a == "-maxSetSize" || a == "-lncheck") && i + 1 < argc) {
+            i++; /* TLC tuning / housekeeping flags that have no counterpart here: accepted so existing command lines keep working */
+        } else if (a == "-cleanup" || a == "-nowarning" || a == "-tool" || a == "-terse" || a == "-gzip" || a == "-debug") {
+        } else if (a == "-recover" || a == "-dfid" || a == "-generateSpecTE" || a == "-continue-from") {
+            fprintf(stderr, "Error: %s is not available (no checkpoints, no depth-first iterative deepening, no trace-expression specs)\n", a.c_str());
+            return 255;
+        } else if (a == "-gpu" && i + 1 < argc) o.device = atoi(argv[++i]);
         else if (a == "-table" && i + 1 < argc) o.table_capacity = strtoull(argv[++i], 0, 10);
         else if (a == "-frontier" && i + 1 < argc) o.frontier_capacity = strtoull(argv[++i], 0, 10);
         else if (a == "-continue") o.stop_on_violation = 0;
