@@ -1065,7 +1065,7 @@ def load_vsr(path, R, C, values, L, restart=0):
     return Evaluator(m, consts)
 
 
-def bfs(ev, view="view", invariant=None, max_depth=0, max_states=0):
+def bfs(ev, view="view", invariant=None, max_depth=0, max_states=0, keep_levels=True):
     """TLC-style breadth-first search straight from the module text: states are identified by their VIEW value (first
     arrival represents the class, as in TLC), every successor found counts as generated.  No symmetry reduction.
     Returns dict(level_sizes, level_generated, generated, distinct, depth, violation_depth, levels=[[state, ...], ...])."""
@@ -1102,7 +1102,8 @@ def bfs(ev, view="view", invariant=None, max_depth=0, max_states=0):
         if not nxt:
             break
         out["level_sizes"].append(len(nxt))
-        out["levels"].append(nxt)
+        if keep_levels:
+            out["levels"].append(nxt)
         out["distinct"] += len(nxt)
         out["depth"] += 1
         frontier = nxt

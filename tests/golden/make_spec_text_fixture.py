@@ -34,7 +34,7 @@ import spec_text as S  # noqa: E402
 
 def space_row(R, V, L, depth):
     t = time.time()
-    r = S.T.bfs(S.evaluator(R, V, L), invariant="AcknowledgedWriteNotLost", max_depth=depth)
+    r = S.T.bfs(S.evaluator(R, V, L), invariant="AcknowledgedWriteNotLost", max_depth=depth, keep_levels=False)
     row = dict(R=R, V=V, L=L, max_depth=depth, complete=depth == 0, level_sizes=r["level_sizes"], level_generated=r["level_generated"],
                distinct=r["distinct"], generated=r["generated"], depth=r["depth"], violation_depth=r["violation_depth"],
                states_with_an_ambiguous_choose=r["ambiguous_choose"], seconds=round(time.time() - t, 1))
