@@ -38,11 +38,12 @@ class ModelValue:
 
 class Fn:
     """a TLA+ function with a finite domain: records (string keys), sequences/tuples (keys 1..n), bags, ..."""
-    __slots__ = ("d", "_h")
+    __slots__ = ("d", "_h", "_k")
 
     def __init__(self, d):
         self.d = d
         self._h = None
+        self._k = None
 
     def __hash__(self):
         if self._h is None:
@@ -87,7 +88,9 @@ def vkey(v):
     if isinstance(v, frozenset):
         return (4, len(v), tuple(sorted(vkey(x) for x in v)))
     if isinstance(v, Fn):
-        return (5, len(v.d), tuple(sorted((vkey(k), vkey(x)) for k, x in v.d.items())))
+        if v._k is None:
+            v._k = (5, len(v.d), tuple(sorted((vkey(k), vkey(x)) for k, x in v.d.items())))
+        return v._k
     raise EvalError("no order for %r" % (v,))
 
 

@@ -15,12 +15,12 @@
  *   E7  invariant               evaluated inline on every newly inserted state
  *   E8  trace                   (parent id, candidate) per new state
  *   E9  deadlock                states with no enabled candidate
- * Work shape: a block takes 32*WARPS frontier states, one per thread.  SCAN: all warps walk Next's 13
- * action groups together (a barrier per group); every thread evaluates that group's guards on its own state (the
- * candidate index is warp-uniform, so is the control flow) and enabled (state, candidate) pairs are ballot-compacted
- * into a block pool, which ends up grouped by action.  APPLY: warps take batches of 32 pairs of ONE action and apply
- * them one per lane — the successor is built in a rotated shared-memory row, fingerprinted, probed, inserted — so the
- * expensive part runs with full lanes, without divergence between actions, and with one action's code live at a time.
+ * Work shape: a block takes 32*WARPS frontier states, one per thread.  SCAN: every thread copies its state
+ * into registers and evaluates all guards of Next on it with compile-time candidate indices (Ops::enabled_group): one bit
+ * per (action, binding); the enabled (state, candidate) pairs are written to a block pool grouped by action (packed warp
+ * prefix sums, one shared atomic per warp and action group, one barrier).  APPLY: warps take batches of 32 pairs of ONE
+ * action and apply them one per lane — the successor is built in a rotated shared-memory row, read once into registers,
+ * fingerprinted, probed, inserted — so the expensive part runs with full lanes and without divergence between actions.
  * See profiles/round1_expand_kernel.md for the measurements that led here.
  */
 #ifndef VSR_GPU_CUH
@@ -220,7 +220,7 @@ template <class L, int WARPS> struct BlockSmemT {
     uint64_t fp_tab[8 * 256];                    /* FP64 slicing-by-8 tables */
     uint32_t par[NS * (L::NW + 1)];              /* parents, row stride NW+1 (odd: bank-conflict-free column reads) */
     static constexpr int QCAP = QPS * NS;
-    uint16_t pool[QCAP];                         /* enabled (state, candidate) pairs, grouped by action (a barrier per group) */
+    uint16_t pool[QCAP];                         /* enabled (state, candidate) pairs, grouped by action */
     int qcount[NG];                              /* pairs found per group (may exceed what the pool holds) */
     int take;
     unsigned long long round_first;
