@@ -207,7 +207,11 @@ constexpr int QPS = 10;       /* pool entries per parent state (pool = QPS * sta
 #endif
 
 template <class L> struct WarpStage {
+#ifdef VSR_EXP_SKEW
+    alignas(16) uint32_t stage[SCAP * L::NW + 32]; /* + room for the skew of the scratch rows (Expander::scratch) */
+#else
     alignas(16) uint32_t stage[SCAP * L::NW];    /* new states, packed back to back for the bulk store */
+#endif
     unsigned long long tstage[SCAP];             /* their trace records */
     /* per-warp running state.  It lives here, not in the Expander object: the big per-action routines are real calls
        (one copy of each in the instruction cache), and an object whose address is passed to them would be kept in
@@ -300,10 +304,20 @@ template <class L> struct Expander {
     }
 
     /* fingerprint, route, insert, stage: the part of apply that does not depend on the action */
+#ifdef VSR_EXP_SKEW
+    /* experiment: plain rows, bank conflicts avoided by skewing the row STARTS instead of rotating every access.  Rows of
+       NW words collide every p = 32 / gcd(NW, 32) lanes; shifting lane l's row by l / p words puts the 32 lanes' word i in
+       32 different banks, and an access is base + i: no per-access arithmetic. */
+    typedef uint32_t* Row;
+    static constexpr int gcd32(int a) { int g = 32; while (a % g) g >>= 1; return g; }
+    static constexpr int SKEW_P = 32 / gcd32(L::NW);
+    static __device__ __forceinline__ Row scratch(WarpStage<L>& S, int lane) { return &S.stage[(32 + lane) * L::NW + lane / SKEW_P]; }
+#else
     typedef SwzRow<L::NW> Row;
     /* this lane's scratch row for the successor it builds: staging rows 32..63 are free whenever a batch starts
        (fewer than 32 states are staged then), rotated by the lane so equal word indices fall in different banks */
     static __device__ __forceinline__ Row scratch(WarpStage<L>& S, int lane) { return Row{&S.stage[(32 + lane) * L::NW], lane % L::NW}; }
+#endif
 
     /* returns this lane's counts for the run's statistics: successors generated (low half) | seen-set probes (high half);
        the caller keeps the running sums in registers (a warp reduction per batch cost 25 shuffles) */
