@@ -1071,6 +1071,7 @@ def load_vsr(path, R, C, values, L, restart=0):
 def bfs(ev, view="view", invariant=None, max_depth=0, max_states=0, keep_levels=True):
     """TLC-style breadth-first search straight from the module text: states are identified by their VIEW value (first
     arrival represents the class, as in TLC), every successor found counts as generated.  No symmetry reduction.
+    `invariant`: a definition name or a list of them, evaluated on every new state.
     Returns dict(level_sizes, level_generated, generated, distinct, depth, violation_depth, levels=[[state, ...], ...])."""
     init = ev.initial_states()
     seen = set()
@@ -1082,7 +1083,8 @@ def bfs(ev, view="view", invariant=None, max_depth=0, max_states=0, keep_levels=
             frontier.append(st)
     out = dict(level_sizes=[len(frontier)], level_generated=[], generated=len(init), distinct=len(frontier), depth=1, violation_depth=0,
                levels=[list(frontier)], ambiguous_choose=0, deadlock_depth=0)
-    if invariant and any(not ev.holds(invariant, st) for st in frontier):
+    invs = [invariant] if isinstance(invariant, str) else list(invariant or ())
+    if any(not ev.holds(i, st) for st in frontier for i in invs):
         out["violation_depth"] = 1
     while frontier and not (max_depth and out["depth"] >= max_depth) and not (max_states and out["distinct"] >= max_states):
         nxt, gen = [], 0
@@ -1097,7 +1099,7 @@ def bfs(ev, view="view", invariant=None, max_depth=0, max_states=0, keep_levels=
                 if k not in seen:
                     seen.add(k)
                     nxt.append(sp)
-                    if invariant and not out["violation_depth"] and not ev.holds(invariant, sp):
+                    if invs and not out["violation_depth"] and not all(ev.holds(i, sp) for i in invs):
                         out["violation_depth"] = out["depth"] + 1
             out["ambiguous_choose"] += 1 if ev.choose_log else 0
         out["level_generated"].append(gen)

@@ -221,3 +221,22 @@ def test_oracle_equals_the_committed_spec_text_results():
         assert o.level_generated[:len(row["level_generated"])] == row["level_generated"], (R, V, L)
         if row["complete"]:
             assert (o.distinct, o.generated, o.depth) == (row["distinct"], row["generated"], row["depth"])
+
+
+@needs_reference
+def test_the_evaluator_also_runs_the_state_transfer_analysis_spec():
+    """SURVEY §8(f) item 3 names analysis/03-state-transfer/VR_STATE_TRANSFER.tla (the repaired state transfer) as the next
+    spec to lower.  Its oracle exists already: the text evaluator executes that module unchanged with its cfg's constants
+    (VR_STATE_TRANSFER.cfg:3-19) — here a breadth-first prefix with the cfg's three invariants."""
+    import spec_text as S
+    T = S.T
+    path = os.path.join(os.path.dirname(S.SPEC), "analysis", "03-state-transfer", "VR_STATE_TRANSFER.tla")
+    m = T.Module(open(path).read())
+    consts = {"ReplicaCount": 3, "Values": frozenset(T.ModelValue(v) for v in ("v1", "v2")), "StartViewOnTimerLimit": 2,
+              "NoProgressChangeLimit": 0}
+    for c in m.constants:
+        consts.setdefault(c, T.ModelValue(c))
+    ev = T.Evaluator(m, consts)
+    r = T.bfs(ev, invariant=("AcknowledgedWritesExistOnMajority", "NoLogDivergence", "CommitNumberNeverHigherThanOpNumber"),
+              max_depth=6, keep_levels=False)
+    assert r["level_sizes"] == [1, 4, 17, 63, 238, 851] and r["violation_depth"] == 0
