@@ -14,7 +14,7 @@
  * Second pin: the reference's own SOURCE TEXT.  oracle/tla_eval.py parses VSR.tla as it lies under
  * /root/reference and enumerates Init/Next the way TLC does; tests/test_spec_text.py compares it with
  * this file — complete state spaces level by level (cfg1 = BASELINE configs[0]: 76 distinct / 100
- * generated / depth 14, and six more up to 697,364 states), successor sets state by state along the golden trace,
+ * generated / depth 14, and eight more up to 697,364 states), successor sets state by state along the golden trace,
  * random walks on cfg2/cfg3/cfg4 constants, the recovery actions with RestartEmptyLimit 1 and 2, both
  * safety invariants, orbit counts under SYMMETRY: 0 differences (tests/golden/spec_text_results.json).
  * Still "parity unpinned": TLC's FINGERPRINT values (its value serialisation and model-value intern
