@@ -104,6 +104,7 @@ static bool load_layout_plugin(int R, int V, int K, LayoutPlugin* out, std::stri
     const char* jit = getenv("VSR_B200_JIT");
     if (jit && jit[0] == '0') { why = "not built in, no usable " + path + (open_why.empty() ? "" : " (" + open_why + ")") + ", and VSR_B200_JIT=0"; return false; }
     if (!mtime_of(src)) { why = "not built in, and the plug-in source " + src + " is not installed"; return false; }
+    if (dir.find('\'') != std::string::npos) { why = "not built in, and the library path contains a quote character (the compile command cannot name it)"; return false; }
     mkdir(ldir.c_str(), 0755);
     const std::string lock = path + ".lock";
     const int fd = open(lock.c_str(), O_CREAT | O_RDWR, 0644);
