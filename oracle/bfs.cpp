@@ -39,7 +39,7 @@ struct Slot {
     uint32_t level;
     uint32_t pending; /* index into the shard's pending list while level == current */
 };
-constexpr int NSHARD = 64;
+constexpr int NSHARD = 256; /* >= the thread count of a big host: the insert phase hands out whole shards */
 struct Shard {
     std::unordered_map<Dig, Slot, DigHash> map;
     std::vector<Cand> pending;
@@ -112,7 +112,9 @@ BfsResult bfs(const Params& p, const BfsOptions& o) {
         if (o.max_seconds > 0 && now_s() - t0 >= o.max_seconds) { stopped_early = true; break; }
         const int cur = level + 1; /* depth of the states generated now */
         uint64_t gen_this = 0;
-        const size_t BATCH = 1 << 15;
+        /* states per parallel region: enough per thread that starting and joining the threads does not dominate on a
+           many-core host (bench.py's CPU baseline runs this with every core of the box) */
+        const size_t BATCH = std::max<size_t>(1 << 15, (size_t)W << 12);
         std::atomic<uint64_t> h2{0};
         std::atomic<uint64_t> dead{(uint64_t)-1};
         std::vector<Assumptions> was(W);
