@@ -21,8 +21,9 @@ build base ""
 build emit_uv "-DVSR_EXP_EMIT_UV"
 build home_lowbits "-DVSR_EXP_HOME_LOWBITS"
 build prefetch "-DVSR_EXP_PREFETCH"
+build par128 "-DVSR_EXP_PAR128"           # parents loaded 16 bytes at a time
 build skew "-DVSR_EXP_SKEW"               # scratch rows skewed, not rotated: apply<G> bodies 20 % smaller
-build all4 "-DVSR_EXP_EMIT_UV -DVSR_EXP_HOME_LOWBITS -DVSR_EXP_PREFETCH -DVSR_EXP_SKEW"
+build all5 "-DVSR_EXP_EMIT_UV -DVSR_EXP_HOME_LOWBITS -DVSR_EXP_PREFETCH -DVSR_EXP_SKEW -DVSR_EXP_PAR128"
 build warps12 "-DVSR_FORCE_WARPS=12"     # 80 registers per thread, 24 warps per SM
 build warps8 "-DVSR_FORCE_WARPS=8"       # 128 registers per thread
 build qps1 "-DVSR_QPS=1"                 # correctness variant: VSR_B200_LIB=...qps1.so python -m pytest tests/test_gpu_parity.py -k "3-2-2 or deterministic"

@@ -579,7 +579,19 @@ template <class L> struct Expander {
     __device__ void run_round(unsigned long long first, int count) {
         /* coalesced load of `count` parent states into padded rows */
         const uint32_t* src = P.in + first * L::NW;
+#ifdef VSR_EXP_PAR128 /* experiment: 16-byte loads (states are whole 16-byte units), a quarter of the index arithmetic */
+        {
+            constexpr int Q = L::NW / 4;
+            const uint4* src4 = reinterpret_cast<const uint4*>(src);
+            for (int i = tid; i < count * Q; i += NS) {
+                const uint4 v = __ldg(src4 + i);
+                uint32_t* d = &B.par[(i / Q) * (L::NW + 1) + (i % Q) * 4];
+                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            }
+        }
+#else
         for (int i = tid; i < count * L::NW; i += NS) B.par[(i / L::NW) * (L::NW + 1) + (i % L::NW)] = __ldg(src + i);
+#endif
         if (tid < Smem::NG) B.qcount[tid] = 0;
         if (tid == 0) { B.round_first = first; B.take = 0; }
         __syncthreads();
