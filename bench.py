@@ -232,10 +232,14 @@ def main():
     ev0.record()
     t0 = time.time()
     kernel_ms = 0.0
+    insert_ms = 0.0
+    exchanged = 0
     levels_ms = []
     for _ in range(args.steps):
         res = one_step()
         kernel_ms += res.kernel_ms_max
+        insert_ms += res.insert_ms_max
+        exchanged += res.exchanged_records
         st = eng.stats()
         launches0 += int(st.kernel_launches)
         levels_ms.append([float(st.level_ms[i]) for i in range(int(st.num_levels))])
@@ -321,6 +325,10 @@ def main():
                        "device time between CUDA events on the launch stream = %.3f s" % (dev_ms / 1e3)},
             "gpu_launches": launches0,
             "kernel_seconds": kern_s,
+            # N>1: the part of kernel_seconds spent in insert_kernel on records received from peers (slowest rank per level),
+            # and the records rank 0 shipped: what the exchange costs next to the expansion
+            "kernel_seconds_insert": insert_ms / 1e3,
+            "records_sent_rank0": exchanged,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "traffic_note": "launches differ in size, so no single per-launch figure: the ncu --set full capture of two mid-size "
                                          "wavefronts (profiles/round1_expand_kernel.md) measured dram read+write = 1.58x the algorithmic bytes",

@@ -166,7 +166,8 @@ typedef struct VsrLevelInfo {
     uint64_t new_states, generated, frontier_in, ties, collisions;
     int32_t violation, deadlock, error_code, overflow;
     uint64_t violation_id, deadlock_id;
-    double ms;
+    double ms;        /* kernel time of the level on this rank (expand + insert), CUDA events on the launch stream */
+    double ms_insert; /* of which insert_kernel (records received from peers; 0 on a single rank after Init) */
 } VsrLevelInfo;
 int vsr_engine_finish_level(VsrEngine* e, VsrLevelInfo* out);
 uint64_t vsr_engine_frontier_size(const VsrEngine* e);

@@ -103,6 +103,7 @@ BfsResult bfs(const Params& p, const BfsOptions& o) {
         }
     }
     int level = 1;
+    double t_expand = 0, t_insert = 0, t_collect = 0; /* ORC_BFS_PROFILE=1: where the wall time of a run went */
     uint64_t violating_id = (uint64_t)-1, deadlock_id = (uint64_t)-1;
     bool stopped_early = false;
 
@@ -147,12 +148,15 @@ BfsResult bfs(const Params& p, const BfsOptions& o) {
                     }
                 }
             };
+            double tp0 = now_s();
             {
                 std::vector<std::thread> th;
                 for (int w = 1; w < W; w++) th.emplace_back(expand, w);
                 expand(0);
                 for (auto& t : th) t.join();
             }
+            double tp1 = now_s();
+            t_expand += tp1 - tp0;
             gen_this += gen.load();
             expanded = b1;
             /* insert phase: one shard at a time per thread */
@@ -185,6 +189,7 @@ BfsResult bfs(const Params& p, const BfsOptions& o) {
                 insert();
                 for (auto& t : th) t.join();
             }
+            t_insert += now_s() - tp1;
             if (o.max_seconds > 0 && now_s() - t0 >= o.max_seconds && b1 < frontier.size()) stopped_early = true;
         }
         for (const Assumptions& a : was) {
@@ -196,6 +201,7 @@ BfsResult bfs(const Params& p, const BfsOptions& o) {
         res.level_generated.push_back(gen_this);
 
         /* collect the new level in digest order */
+        double tc0 = now_s();
         std::vector<Cand*> fresh;
         for (Shard& S : shards)
             for (Cand& c : S.pending) fresh.push_back(&c);
@@ -225,6 +231,7 @@ BfsResult bfs(const Params& p, const BfsOptions& o) {
         }
         for (Shard& S : shards) { S.pending.clear(); S.pending.shrink_to_fit(); }
         res.distinct += next_frontier.size();
+        t_collect += now_s() - tc0;
         if (stopped_early) {
             /* partial level: report what was found, queue = unexpanded part + new states */
             res.queue = (frontier.size() - expanded) + next_frontier.size();
@@ -243,6 +250,8 @@ BfsResult bfs(const Params& p, const BfsOptions& o) {
         if (res.rc != 0) break;
     }
     if (dig_file) fclose(dig_file);
+    if (getenv("ORC_BFS_PROFILE"))
+        fprintf(stderr, "orc bfs: %d threads, expand %.2f s, insert %.2f s, collect (serial) %.2f s\n", W, t_expand, t_insert, t_collect);
     res.depth = level;
     if (res.rc == 0 && !stopped_early) res.complete = true;
     if (res.rc != 0 || (stopped_early && res.queue == 0)) res.queue = frontier.size();

@@ -75,6 +75,7 @@ struct VsrEngine {
     bool level_open = false;     /* counters reset for the level being generated */
     VsrStats st;
     double level_ms_acc = 0;
+    double level_ms_insert_acc = 0; /* the part of level_ms_acc spent in insert_kernel (records from peers) */
     std::vector<std::vector<uint8_t>> collected; /* per level states (collect_levels) */
     char last_error[256] = {0};
 };
@@ -87,6 +88,7 @@ static int engine_reset_level(VsrEngine* e) {
     if (e->send_count) CK(cudaMemsetAsync(e->send_count, 0, sizeof(unsigned int) * e->world, e->stream));
     e->level_open = true;
     e->level_ms_acc = 0;
+    e->level_ms_insert_acc = 0;
     return 0;
 }
 
@@ -321,6 +323,7 @@ int vsr_engine_insert_records(VsrEngine* e, const void* dev_records, uint64_t n)
     float ms = 0;
     cudaEventElapsedTime(&ms, e->ev0, e->ev1);
     e->level_ms_acc += ms;
+    e->level_ms_insert_acc += ms;
     return 0;
 }
 
@@ -381,6 +384,7 @@ int vsr_engine_finish_level(VsrEngine* e, VsrLevelInfo* out) {
     li.error_code = c.error;
     li.overflow = c.overflow;
     li.ms = e->level_ms_acc;
+    li.ms_insert = e->level_ms_insert_acc;
     if (c.overflow) {
         snprintf(e->last_error, sizeof e->last_error, "capacity exceeded (%s): %llu new states this level, frontier capacity %llu",
                  c.overflow == 1 ? "frontier" : (c.overflow == 2 ? "tie list" : (c.overflow == 3 ? "send buffer" : "seen-set")), (unsigned long long)c.out_count,

@@ -135,6 +135,7 @@ class ShardedResult:
     violation_gid: int = -1
     seconds: float = 0.0
     kernel_ms_max: float = 0.0       # sum over levels of the slowest rank's kernel time
+    insert_ms_max: float = 0.0       # of which insert_kernel (records from peers), slowest rank per level
     exchanged_records: int = 0       # records this rank sent
     launches: int = 0
     trace_cands: List[int] = field(default_factory=list)
@@ -221,8 +222,9 @@ class ShardedBfs:
             vmin, dmin = self._allreduce(
                 [(self.rank << GID_SHIFT) | int(li.violation_id) if li.violation else I64_MAX,
                  (self.rank << GID_SHIFT) | int(li.deadlock_id) if li.deadlock else I64_MAX], MIN)
-            (kms,) = self._allreduce([int(li.ms * 1e6)], MAX)
+            kms, ims = self._allreduce([int(li.ms * 1e6), int(getattr(li, "ms_insert", 0.0) * 1e6)], MAX)
             r.kernel_ms_max += kms / 1e6
+            r.insert_ms_max += ims / 1e6
             r.generated += gen
             r.distinct += new
             r.h2_ties += ties
