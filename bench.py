@@ -329,6 +329,7 @@ def main():
             # and the records rank 0 shipped: what the exchange costs next to the expansion
             "kernel_seconds_insert": insert_ms / 1e3,
             "records_sent_rank0": exchanged,
+            "phase_seconds_rank0_last_step": {k: round(v, 6) for k, v in res.phase_seconds.items()},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "traffic_note": "launches differ in size, so no single per-launch figure: the ncu --set full capture of two mid-size "
                                          "wavefronts (profiles/round1_expand_kernel.md) measured dram read+write = 1.58x the algorithmic bytes",

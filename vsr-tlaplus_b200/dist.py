@@ -137,6 +137,9 @@ class ShardedResult:
     kernel_ms_max: float = 0.0       # sum over levels of the slowest rank's kernel time
     insert_ms_max: float = 0.0       # of which insert_kernel (records from peers), slowest rank per level
     exchanged_records: int = 0       # records this rank sent
+    # this rank's host wall clock by phase (every engine call returns after its kernel has finished): expand, exchange
+    # (counts + records, until the last record has arrived), insert, finish (tie resolution, counters, the level's all-reduces)
+    phase_seconds: dict = field(default_factory=lambda: {"expand": 0.0, "exchange": 0.0, "insert": 0.0, "finish": 0.0})
     launches: int = 0
     trace_cands: List[int] = field(default_factory=list)
     trace: List[Tuple[str, bytes]] = field(default_factory=list)
@@ -153,6 +156,7 @@ class ShardedBfs:
         # NCCL moves device tensors; gloo (CPU tests, and ranks that share one GPU in a test) gets host tensors
         self._nccl = world > 1 and dist.get_backend(group) == "nccl"
         self._cdev = getattr(engine, "dev", torch.device("cpu")) if self._nccl else torch.device("cpu")
+        self._phase = {"expand": 0.0, "exchange": 0.0, "insert": 0.0, "finish": 0.0}
 
     # -- collectives (no-ops when world == 1) ---------------------------------------------------
     def _allreduce(self, vals: List[int], op) -> List[int]:
@@ -166,6 +170,7 @@ class ShardedBfs:
         """counts all-to-all, then the records; returns the number of records this rank sent"""
         if self.world == 1:
             return 0
+        tx = time.time()
         counts = self.e.send_counts().to(self._cdev)  # int64[world]
         if int(counts.max()) > self.e.send_capacity:
             raise ck.VsrError(152, f"send buffer overflow: {int(counts.max())} records for one destination, capacity "
@@ -200,7 +205,12 @@ class ShardedBfs:
                                    group=self.group)
             if hout is not out:
                 out.copy_(hout)
+        if self._nccl:
+            torch.cuda.current_stream(self._cdev).synchronize()  # insert() waits for the records anyway: wait here, so the clock splits
+        ti = time.time()
         self.e.insert(recv, total)
+        self._phase["exchange"] += ti - tx
+        self._phase["insert"] += time.time() - ti
         return sum(sc)
 
     # -- the loop -----------------------------------------------------------------------------------
@@ -211,9 +221,11 @@ class ShardedBfs:
         t0 = time.time()
         self.e.reset()
         self.e.seed()
+        self._phase = r.phase_seconds
         level = 0
         bad_gid, result = -1, 0
         while True:
+            tf = time.time()
             li = self.e.finish()
             level += 1
             new, gen, ties, coll, viol, dead, err, ovf, fin = self._allreduce(
@@ -225,6 +237,7 @@ class ShardedBfs:
             kms, ims = self._allreduce([int(li.ms * 1e6), int(getattr(li, "ms_insert", 0.0) * 1e6)], MAX)
             r.kernel_ms_max += kms / 1e6
             r.insert_ms_max += ims / 1e6
+            self._phase["finish"] += time.time() - tf
             r.generated += gen
             r.distinct += new
             r.h2_ties += ties
@@ -262,13 +275,17 @@ class ShardedBfs:
                 if late:
                     break
             if self.world == 1 or not self.part_states:
+                te = time.time()
                 self.e.expand()
+                self._phase["expand"] += time.time() - te
                 r.exchanged_records += self._exchange()
             else:
                 # wide level: pump it in sub-wavefronts so the exchange buffers stay bounded
                 (nparts,) = self._allreduce([(self.e.frontier_size() + self.part_states - 1) // self.part_states], MAX)
                 for k in range(max(nparts, 1)):
+                    te = time.time()
                     self.e.expand_part(k * self.part_states, self.part_states)
+                    self._phase["expand"] += time.time() - te
                     r.exchanged_records += self._exchange()
         r.rc = result
         r.depth = len(r.level_sizes)
