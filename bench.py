@@ -88,6 +88,30 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def usable_cores():
+    """Threads the CPU arm may really use: the affinity mask and a cgroup CPU quota both cap os.cpu_count() in a container."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max",):
+        try:
+            quota, period = open(path).read().split()[:2]
+            if quota != "max":
+                n = min(n, max(1, int(int(quota) / int(period))))
+        except (OSError, ValueError):
+            pass
+    try:
+        q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        if q > 0 and p > 0:
+            n = min(n, max(1, q // p))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
+
+
 def oracle_sample(seconds, workers):
     """CPU restatement (oracle/) on the same workload for a bounded time: distinct states / s on `workers` threads."""
     so = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
@@ -139,7 +163,7 @@ def run_reference(args, rank):
         return
     tlc = try_tlc(30.0)
     if tlc:
-        cores = os.cpu_count() or 1
+        cores = usable_cores()
         print(json.dumps({
             "impl": "reference", "metric": "unique states explored/sec (VSR.tla, shipped VSR.cfg constants)", "value": tlc["rate"],
             "unit": "states/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": 1e3 * tlc["seconds"], "higher_is_better": True,
@@ -149,7 +173,7 @@ def run_reference(args, rank):
                              "sample": "tlc2.TLC for %.0f s: %d distinct states" % (tlc["seconds"], tlc["distinct"])},
             "e2e": {"value": tlc["rate"], "unit": "states/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     per_step = 10.0
     for _ in range(args.warmup):
         oracle_sample(1.0, cores)
@@ -341,9 +365,11 @@ def main():
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
+            cores = usable_cores()
             s = oracle_sample(args.cpu_seconds, cores)
+            s1 = oracle_sample(min(3.0, args.cpu_seconds), 1) if cores > 1 else s
             out["cpu_baseline"] = {"value": s["rate"], "unit": "states/s", "cores": cores, "kind": "port",
+                                   "single_thread_value": s1["rate"],  # the same BFS on one thread for 3 s: how far the all-core figure is from linear
                                    "sample": "CPU restatement (oracle/, not TLC) BFS of the same config for %.0f s: depth %d, %d distinct states"
                                              % (args.cpu_seconds, s["depth"], s["distinct"])}
         print(json.dumps(out))
