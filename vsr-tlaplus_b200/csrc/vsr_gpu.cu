@@ -6,6 +6,7 @@
  * There is NO CPU fallback: without a usable CUDA device every entry point returns 153.
  */
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -193,7 +194,12 @@ int vsr_engine_create(const VsrModel* m, const VsrRunOpts* opts, int rank, int w
     if ((ce = cudaMallocAsync((void**)&e->ties, e->tie_cap * (size_t)e->g->tie_bytes, e->stream)) != cudaSuccess) return bail("cudaMalloc", ce);
     if ((ce = cudaMallocAsync((void**)&e->fp_tab, 8 * 256 * 8, e->stream)) != cudaSuccess) return bail("cudaMalloc", ce);
     if (world > 1) { /* sender-side duplicate filter: 1/8 of the seen-set's slots, 8 B each */
-        e->sent_cap = tcap / 8 < (1ull << 16) ? (1ull << 16) : tcap / 8;
+        uint64_t div = 8; /* tuning hook VSR_SENT_FILTER_DIV = 1, 2, 4 ... 64: a larger filter ships fewer duplicates (memory permitting) */
+        if (const char* s = getenv("VSR_SENT_FILTER_DIV")) {
+            const long d = strtol(s, nullptr, 10);
+            if (d >= 1 && d <= 64 && (d & (d - 1)) == 0) div = (uint64_t)d;
+        }
+        e->sent_cap = tcap / div < (1ull << 16) ? (1ull << 16) : tcap / div;
         if ((ce = cudaMallocAsync((void**)&e->sent_cache, e->sent_cap * 8, e->stream)) != cudaSuccess) return bail("cudaMalloc(sent filter)", ce);
         if ((ce = cudaMemsetAsync(e->sent_cache, 0, e->sent_cap * 8, e->stream)) != cudaSuccess) return bail("memset", ce);
     }
