@@ -10,7 +10,10 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
+#include <functional>
 #include <mutex>
 #include <thread>
 #include <unordered_map>
@@ -44,6 +47,66 @@ struct Shard {
     std::unordered_map<Dig, Slot, DigHash> map;
     std::vector<Cand> pending;
 };
+/* W workers that live as long as the BFS (worker 0 is the caller).  Persistent on purpose: a thread keeps its malloc arena,
+   so what worker w allocated in one phase it can free in a later one without taking another thread's arena lock, and a
+   many-core host does not start 2 x W threads per batch. */
+class Pool {
+public:
+    explicit Pool(int w) : W(w) {
+        for (int i = 1; i < W; i++) th.emplace_back([this, i] { loop(i); });
+    }
+    ~Pool() {
+        {
+            std::lock_guard<std::mutex> g(m);
+            stop = true;
+            gen++;
+        }
+        cv.notify_all();
+        for (auto& t : th) t.join();
+    }
+    /* runs f(w) on every worker w in 0..W-1 and returns when all have finished */
+    void run(const std::function<void(int)>& f) {
+        {
+            std::lock_guard<std::mutex> g(m);
+            fn = &f;
+            pending = W - 1;
+            gen++;
+        }
+        cv.notify_all();
+        f(0);
+        std::unique_lock<std::mutex> g(m);
+        done.wait(g, [this] { return pending == 0; });
+        fn = nullptr;
+    }
+private:
+    void loop(int w) {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int)>* f;
+            {
+                std::unique_lock<std::mutex> g(m);
+                cv.wait(g, [&] { return gen != seen; });
+                seen = gen;
+                if (stop) return;
+                f = fn;
+            }
+            (*f)(w);
+            {
+                std::lock_guard<std::mutex> g(m);
+                if (--pending == 0) done.notify_one();
+            }
+        }
+    }
+    const int W;
+    std::vector<std::thread> th;
+    std::mutex m;
+    std::condition_variable cv, done;
+    const std::function<void(int)>* fn = nullptr;
+    uint64_t gen = 0;
+    int pending = 0;
+    bool stop = false;
+};
+
 double now_s() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -54,6 +117,7 @@ BfsResult bfs(const Params& p, const BfsOptions& o) {
     double t0 = now_s();
     std::vector<Shard> shards(NSHARD);
     int W = std::max(1, o.workers);
+    Pool pool(W);
 
     /* global per-state trace records */
     std::vector<uint64_t> parent_of;
@@ -149,19 +213,14 @@ BfsResult bfs(const Params& p, const BfsOptions& o) {
                 }
             };
             double tp0 = now_s();
-            {
-                std::vector<std::thread> th;
-                for (int w = 1; w < W; w++) th.emplace_back(expand, w);
-                expand(0);
-                for (auto& t : th) t.join();
-            }
+            pool.run(expand);
             double tp1 = now_s();
             t_expand += tp1 - tp0;
             gen_this += gen.load();
             expanded = b1;
             /* insert phase: one shard at a time per thread */
             std::atomic<int> next_shard{0};
-            auto insert = [&]() {
+            auto insert = [&](int) {
                 for (;;) {
                     int sh = next_shard.fetch_add(1);
                     if (sh >= NSHARD) break;
@@ -183,12 +242,9 @@ BfsResult bfs(const Params& p, const BfsOptions& o) {
                         }
                 }
             };
-            {
-                std::vector<std::thread> th;
-                for (int w = 1; w < W; w++) th.emplace_back(insert);
-                insert();
-                for (auto& t : th) t.join();
-            }
+            pool.run(insert);
+            /* the losers (most candidates are duplicates) go back to the arena of the worker that made them */
+            pool.run([&](int w) { std::vector<std::vector<Cand>>().swap(buckets[w]); });
             t_insert += now_s() - tp1;
             if (o.max_seconds > 0 && now_s() - t0 >= o.max_seconds && b1 < frontier.size()) stopped_early = true;
         }
