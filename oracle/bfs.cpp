@@ -17,6 +17,9 @@
 #include <mutex>
 #include <thread>
 #include <unordered_map>
+#ifdef __GLIBC__
+#include <malloc.h>
+#endif
 
 #include "vsr_oracle.h"
 
@@ -117,6 +120,17 @@ BfsResult bfs(const Params& p, const BfsOptions& o) {
     double t0 = now_s();
     std::vector<Shard> shards(NSHARD);
     int W = std::max(1, o.workers);
+#ifdef __GLIBC__
+    if (const char* mo = getenv("ORC_BFS_MALLOPT")) {
+        /* allocator tuning for the timed CPU baseline only (bench.py tries both settings and keeps the faster): every successor
+           is a fresh graph of small heap objects; "1" keeps the arenas from handing pages back and asking for them again (each
+           shrink/grow is an mprotect/madvise under the process-wide mmap lock, which a many-thread run queues on), "0" restores
+           glibc's defaults.  Process-wide and sticky, hence opt-in. */
+        const bool on = mo[0] == '1';
+        mallopt(M_TRIM_THRESHOLD, on ? 1 << 30 : 128 << 10);
+        mallopt(M_MMAP_THRESHOLD, on ? 64 << 20 : 128 << 10);
+    }
+#endif
     Pool pool(W);
 
     /* global per-state trace records */
