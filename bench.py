@@ -365,6 +365,10 @@ def main():
             "kernel_seconds_insert": insert_ms / 1e3,
             "records_sent_rank0": exchanged,
             "phase_seconds_rank0_last_step": {k: round(v, 6) for k, v in res.phase_seconds.items()},
+            # rank 0's kernel time per BFS level (ms, expand + insert) in the last timed step, beside the level sizes: where a
+            # multi-GPU run loses against one GPU (narrow levels are launch- and latency-bound, wide ones exchange-bound)
+            "level_ms_rank0_last_step": [round(x, 4) for x in levels_ms[-1]] if levels_ms else [],
+            "level_sizes": [int(x) for x in res.level_sizes],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "traffic_note": "launches differ in size, so no single per-launch figure: the ncu --set full capture of two mid-size "
                                          "wavefronts (profiles/round1_expand_kernel.md) measured dram read+write = 1.58x the algorithmic bytes",
