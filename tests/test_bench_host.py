@@ -1,0 +1,62 @@
+"""Host-side checks of bench.py that need no GPU: the driver runs bench.py only at round end on the GPU box, so a misspelt
+name there would cost the round's measurement."""
+import builtins
+import os
+import symtable
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _unresolved_globals(path):
+    src = open(path).read()
+    top = symtable.symtable(src, path, "exec")
+    module_names = set(top.get_identifiers())
+    bad = []
+
+    def walk(t):
+        for c in t.get_children():
+            for s in c.get_symbols():
+                if s.is_global() and s.is_referenced() and not s.is_assigned():
+                    n = s.get_name()
+                    if n not in module_names and not hasattr(builtins, n):
+                        bad.append((c.get_name(), n))
+            walk(c)
+
+    walk(top)
+    return bad
+
+
+@pytest.mark.parametrize("rel", ["bench.py", "__graft_entry__.py", "vsr-tlaplus_b200/dist.py", "vsr-tlaplus_b200/checker.py"])
+def test_every_global_name_resolves(rel):
+    assert _unresolved_globals(os.path.join(ROOT, rel)) == []
+
+
+def test_usable_cores_is_within_the_machine():
+    import bench
+    n = bench.usable_cores()
+    assert 1 <= n <= (os.cpu_count() or 1)
+
+
+def test_sharded_result_carries_the_fields_the_bench_line_prints():
+    import _pkg
+    _pkg.load()
+    from vsr_tlaplus_b200 import dist as vdist
+    r = vdist.ShardedResult()
+    assert set(r.phase_seconds) == {"expand", "exchange", "insert", "finish"}
+    assert r.insert_ms_max == 0.0 and r.exchanged_records == 0 and r.level_sizes == []
+
+
+def test_level_reduce_on_one_rank_is_the_identity():
+    import _pkg
+    _pkg.load()
+    from vsr_tlaplus_b200 import dist as vdist
+
+    class _E:  # no engine call is made by _reduce_level
+        pass
+
+    b = vdist.ShardedBfs(_E(), 0, 1)
+    assert b._reduce_level([1, 2], [3], [4, 5]) == ([1, 2], [3], [4, 5])
