@@ -29,9 +29,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(R=3, V=2, L=2)           # BASELINE configs[1] = vsr-revisited/paper/VSR.cfg
-TABLE_CAP = 1 << 31                      # 2^31 slots * 16 B = 32 GiB (1.17e9 states -> load 0.55) + 15 GiB of trace records
+TABLE_CAP = 1 << int(os.environ.get("VSR_BENCH_TABLE_LOG2", "31"))  # 2^31 slots * 16 B = 32 GiB (1.17e9 states -> load 0.55) + 15 GiB of trace records
 FRONTIER_CAP = 140_000_000               # widest level: 120,193,500 states
 EXPECT = dict(distinct=1173992337, generated=3129587684, depth=47, violation_level=28)
+# a configuration BOTH arms finish: (R=3, V=2, L=1) complete = 697,364 distinct states, depth 30 (pinned to the spec's text,
+# tests/golden/spec_text_results.json) - the same-config comparison beside the bounded cfg2 sample of the CPU arm
+SMALL = dict(R=3, V=2, L=1, distinct=697364, generated=1831657, depth=30)
+# BASELINE configs[2]/[4]: README constants to the first AcknowledgedWriteNotLost violation (needs >= 4 GPUs of memory)
+CFG3 = dict(R=3, V=3, L=3, violation_level=24, distinct=3166753191, table_total=1 << 33, frontier_total=1_600_000_000)
 
 
 def peaks():
@@ -112,13 +117,15 @@ def usable_cores():
     return max(1, n)
 
 
-def oracle_sample(seconds, workers):
-    """CPU restatement (oracle/) on the same workload for a bounded time: distinct states / s on `workers` threads."""
+def oracle_sample(seconds, workers, cfg=None):
+    """CPU restatement (oracle/) on the same workload for a bounded time (0 = to completion): distinct states / s on
+    `workers` threads."""
     so = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
     lib = C.CDLL(so)
     lib.orc_bfs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_double, C.c_int, C.c_int, C.c_int, C.c_char_p,
                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
-    q = (C.c_int * 8)(WORKLOAD["R"], 1, WORKLOAD["V"], WORKLOAD["L"], 0, 1, 1, 0)  # invariant 0: explore, do not stop
+    cfg = cfg or WORKLOAD
+    q = (C.c_int * 8)(cfg["R"], 1, cfg["V"], cfg["L"], 0, 1, 1, 0)  # invariant 0: explore, do not stop
     scal = (C.c_uint64 * 32)()
     lv = (C.c_uint64 * 512)()
     t0 = time.time()
@@ -127,16 +134,13 @@ def oracle_sample(seconds, workers):
     return dict(distinct=int(scal[1]), generated=int(scal[0]), depth=int(scal[3]), seconds=dt, rate=int(scal[1]) / dt)
 
 
-def select_malloc(cores, rounds):
-    """Warm-up of the CPU arm doubles as allocator selection: the same 2 s sample with glibc's default malloc settings and with
-    trimming off (oracle/bfs.cpp, ORC_BFS_MALLOPT); the timed sample uses whichever explored more states."""
-    tuned = {}
-    for mode in ("0", "1"):
-        os.environ["ORC_BFS_MALLOPT"] = mode
-        tuned[mode] = max([oracle_sample(2.0, cores)["rate"] for _ in range(rounds)])
-    best_mode = max(tuned, key=tuned.get)
-    os.environ["ORC_BFS_MALLOPT"] = best_mode
-    return best_mode, tuned
+def small_complete_cpu(cores):
+    """the same-config leg of the CPU arm: (R=3, V=2, L=1) to completion on all cores"""
+    s = oracle_sample(0.0, cores, SMALL)
+    ok = (s["distinct"], s["generated"], s["depth"]) == (SMALL["distinct"], SMALL["generated"], SMALL["depth"])
+    return {"workload": "VSR.tla ReplicaCount=3 Values={v1,v2} StartViewOnTimerLimit=1, COMPLETE state space (%d distinct states, depth %d)"
+                        % (SMALL["distinct"], SMALL["depth"]),
+            "value": s["rate"], "unit": "states/s", "seconds": s["seconds"], "cores": cores, "kind": "port", "results_match_expected": ok}
 
 
 def try_tlc(seconds):
@@ -187,7 +191,8 @@ def run_reference(args, rank):
         return
     cores = usable_cores()
     per_step = 10.0
-    best_mode, tuned = select_malloc(cores, max(1, (args.warmup + 1) // 2))
+    for _ in range(min(args.warmup, 1)):
+        oracle_sample(2.0, cores)
     tot_states, tot_s = 0, 0.0
     sample = None
     for _ in range(args.steps):
@@ -195,8 +200,8 @@ def run_reference(args, rank):
         tot_states += sample["distinct"]
         tot_s += sample["seconds"]
     v = tot_states / tot_s
-    desc = "BFS of the same config from Init for %.0f s wall per step (reaches depth %d, %d distinct states); malloc %s (2 s samples: default %.3g, no-trim %.3g states/s)" % (
-        per_step, sample["depth"], sample["distinct"], "no-trim" if best_mode == "1" else "default", tuned["0"], tuned["1"])
+    desc = "BFS of the same config from Init for %.0f s wall per step (reaches depth %d, %d distinct states)" % (
+        per_step, sample["depth"], sample["distinct"])
     print(json.dumps({
         "impl": "reference", "metric": "unique states explored/sec (VSR.tla, shipped VSR.cfg constants)", "value": v, "unit": "states/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / max(args.steps, 1),
@@ -205,7 +210,60 @@ def run_reference(args, rank):
                                "bounded sample of the BFS", "note": "CPU restatement of the spec (oracle/), NOT TLC: no JVM in this image"},
         "cpu_baseline": {"value": v, "unit": "states/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": v, "unit": "states/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        # a configuration this arm FINISHES: the b200 arm's line carries the same block (same_config_small.gpu)
+        "same_config_small": small_complete_cpu(cores),
     }))
+
+
+def golden_depths(pkg, mc, eng, torch, tdist, world, dev, rank):
+    """BFS depth at which each state of the reference's published 24-state counterexample (tests/golden/
+    state_transfer_trace.json, generated from state_transfer_violation_trace.txt) was first seen; 0 = not in the explored set"""
+    import base64
+    import zlib
+    fx = json.load(open(os.path.join(ROOT, "tests", "golden", "state_transfer_trace.json")))
+    Flat = pkg.checker.VsrFlatState
+    levels = []
+    for s in fx["states"]:
+        packed = mc.pack(Flat.from_buffer_copy(zlib.decompress(base64.b64decode(s["flat_zlib_b64"]))))  # canonical labels
+        lvl, owner = eng.lookup(packed)
+        levels.append(lvl if owner == rank else 0)
+    t = torch.tensor(levels, dtype=torch.int64, device=dev)
+    if world > 1:
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+    return [int(x) for x in t.cpu().tolist()]
+
+
+def cfg3_first_violation(pkg, vdist, torch, tdist, group, rank, world, local, dev, barrier):
+    """BASELINE configs[2]/[4]: the README constants (the config the reference says needs 500 GB of disk and days under TLC)
+    sharded over the job's GPUs, to the first AcknowledgedWriteNotLost violation; the published trace's states must be in
+    the explored set at depths 1..24 and the checker's own counterexample must be a behaviour of Next ending in the violation."""
+    mc = pkg.ModelChecker.from_constants(CFG3["R"], CFG3["V"], CFG3["L"])
+    table_cap = CFG3["table_total"] // world
+    frontier_cap = CFG3["frontier_total"] // world
+    barrier()
+    t0 = time.time()
+    eng = vdist.GpuEngine(mc, rank, world, device=local, table_capacity=table_cap, frontier_capacity=frontier_cap, keep_trace=True, group=group)
+    t1 = time.time()
+    res = eng.run(stop_on_violation=True, want_trace=True)
+    barrier()
+    t2 = time.time()
+    gold = golden_depths(pkg, mc, eng, torch, tdist, world, dev, rank)
+    out = None
+    if rank == 0:
+        trace = vdist.replay_trace(mc, res.trace_cands) if res.rc == 12 else []
+        mc_lit = pkg.ModelChecker.from_constants(CFG3["R"], CFG3["V"], CFG3["L"], symmetry=False)
+        steps_ok = bool(trace) and all(trace[i + 1][1] in [t for t, _, _ in mc_lit.successors(trace[i][1])] for i in range(len(trace) - 1))
+        viol_ok = bool(trace) and mc_lit.invariant(trace[-1][1]) != 0 and all(mc_lit.invariant(s) == 0 for _, s in trace[:-1])
+        out = {"workload": "VSR.tla ReplicaCount=3 Values={v1,v2,v3} StartViewOnTimerLimit=3 (README.md:13-18) to the first AcknowledgedWriteNotLost violation",
+               "n_gpus": world, "rc": res.rc, "violation_depth": res.violation_level, "distinct_states": res.distinct, "states_generated": res.generated,
+               "seconds_bfs": t2 - t1, "seconds_setup": t1 - t0, "kernel_seconds": res.kernel_ms_max / 1e3, "states_per_s": res.distinct / (t2 - t1),
+               "golden_state_depths": gold, "golden_state_depths_ok": gold == list(range(1, 25)),
+               "counterexample_len": len(trace), "counterexample_actions": [a for a, _ in trace],
+               "counterexample_steps_are_next_steps": steps_ok, "counterexample_violates_only_at_end": viol_ok,
+               "h2_ties": res.h2_ties, "fp_collisions": res.fp_collisions,
+               "matches_expected": res.rc == 12 and res.violation_level == CFG3["violation_level"] and res.distinct == CFG3["distinct"]}
+    eng.close()
+    return out
 
 
 def main():
@@ -216,6 +274,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cfg3", action="store_true", help="N >= 4: skip the README-constants first-violation block")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the end-to-end legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -230,21 +290,21 @@ def main():
     from vsr_tlaplus_b200 import dist as vdist
     import torch.distributed as tdist
 
+    group = None
     if world > 1:
         torch.cuda.set_device(local)
         tdist.init_process_group("nccl", device_id=torch.device("cuda", local))
     assert world == args.gpus, "launch with torchrun --nproc-per-node == --gpus"
     dev = torch.device("cuda", local)
+    if world > 1:
+        group = vdist.Group.from_torch()   # the ranks' shared-memory barrier / all-gather (csrc/vsr_group.cpp)
 
     cfg = pkg.cfg_text(WORKLOAD["R"], ["v1", "v2"], WORKLOAD["L"])
     mc = pkg.ModelChecker.from_cfg_text(cfg)
     S = mc.state_bytes
     table_cap = TABLE_CAP // world
     frontier_cap = FRONTIER_CAP // world + 4_000_000
-    send_cap = max(1, (FRONTIER_CAP * 3) // (world * world)) if world > 1 else 1
-    eng = vdist.GpuEngine(mc, rank, world, device=local, table_capacity=table_cap, frontier_capacity=frontier_cap,
-                          send_capacity=send_cap, keep_trace=True)
-    bfs = vdist.ShardedBfs(eng, rank, world)
+    eng = vdist.GpuEngine(mc, rank, world, device=local, table_capacity=table_cap, frontier_capacity=frontier_cap, keep_trace=True, group=group)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -253,7 +313,7 @@ def main():
         torch.cuda.synchronize(dev)
 
     def one_step():
-        return bfs.run(stop_on_violation=False, want_trace=False)
+        return eng.run(stop_on_violation=False, want_trace=False)
 
     for _ in range(args.warmup):
         res = one_step()
@@ -262,7 +322,6 @@ def main():
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    st0 = eng.stats()
     launches0 = 0
     ev0.record()
     t0 = time.time()
@@ -275,9 +334,8 @@ def main():
         kernel_ms += res.kernel_ms_max
         insert_ms += res.insert_ms_max
         exchanged += res.exchanged_records
-        st = eng.stats()
-        launches0 += int(st.kernel_launches)
-        levels_ms.append([float(st.level_ms[i]) for i in range(int(st.num_levels))])
+        launches0 += res.launches
+        levels_ms.append(res.level_ms)
     ev1.record()
     barrier()
     wall = time.time() - t0
@@ -287,6 +345,7 @@ def main():
         tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
     wall = float(t[0])
     clocks = sampler.stop() if rank == 0 else None
+    st = eng.stats()
 
     ok = (res.distinct == EXPECT["distinct"] and res.generated == EXPECT["generated"] and res.depth == EXPECT["depth"] and
           res.violation_level == EXPECT["violation_level"] and res.complete)
@@ -298,18 +357,22 @@ def main():
     kern_s = kernel_ms / 1e3                 # sum over levels of the slowest rank's kernel time, all timed steps
     achieved = (res.distinct / world) * args.steps * b_alg / kern_s / 1e9
     peak, peak_src = peaks()
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "round2_traffic.json")  # ncu --set full dram bytes of one wide level of THIS configuration
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath))
+        except ValueError:
+            traffic = None
 
-    # the seen-set's own ceiling (SURVEY §8d "probe_peak"): the BFS's insert routine alone on random keys, same table size
     probe = None
-    if rank == 0:
-        eng_probe_out = (C.c_double * 3)()
-        torch.cuda.synchronize(dev)
-    # e2e: the public one-call API with host buffers in and out (N=1: vsr_bfs; N>1: the same pump incl. engine creation)
     eng.close()
     del eng
     torch.cuda.empty_cache()
     barrier()
     if rank == 0:
+        # the seen-set's own ceiling (SURVEY §8d "probe_peak"): the BFS's insert routine alone on random keys, same table size
+        eng_probe_out = (C.c_double * 3)()
         nkeys = 1 << 27
         rc = pkg.load_library().vsr_probe_bench(local, table_cap, nkeys, 0.5, 3, eng_probe_out)
         if rc == 0:
@@ -319,10 +382,11 @@ def main():
                      "how": "vsr_probe_bench: %d splitmix64 keys (50%% repeats) into a fresh table of %d slots with the BFS's own "
                             "insert routine, best of 3: %.3f ms; achieved = this rank's seen-set probes per kernel-second of the BFS"
                             % (nkeys, table_cap, eng_probe_out[0])}
-    # e2e is dominated by allocating and clearing tens of GB (cudaMalloc of a 32 GiB seen-set takes 0.05-1.5 s depending on the
-    # box's allocator state), so it is run three times and the median is reported, with all three in the JSON
-    e2e_runs = []
-    for _ in range(3):
+    # e2e: the public one-call API with host buffers in and out: config text -> parse -> allocate (seen-set, frontiers, inboxes)
+    # -> BFS -> stats and counterexample back in host memory -> teardown.  Allocating and clearing tens of GB varies with the
+    # box's allocator state, so three runs, median reported, all three in the JSON.
+    e2e_runs, e2e_states, h2d, d2h = [], 0, 0, 0
+    for _ in range(0 if args.no_e2e else 3):
         barrier()
         te = time.time()
         if world == 1:
@@ -331,20 +395,38 @@ def main():
             ok = ok and r2.distinct == EXPECT["distinct"] and r2.rc == 12 and len(r2.trace) == EXPECT["violation_level"]
         else:
             mc2 = pkg.ModelChecker.from_cfg_text(cfg)
-            eng2 = vdist.GpuEngine(mc2, rank, world, device=local, table_capacity=table_cap, frontier_capacity=frontier_cap,
-                                   send_capacity=send_cap, keep_trace=True)
-            r2 = vdist.ShardedBfs(eng2, rank, world).run(stop_on_violation=False, want_trace=True)
+            eng2 = vdist.GpuEngine(mc2, rank, world, device=local, table_capacity=table_cap, frontier_capacity=frontier_cap, keep_trace=True, group=group)
+            r2 = eng2.run(stop_on_violation=False, want_trace=True)
+            tr = vdist.replay_trace(mc2, r2.trace_cands) if rank == 0 else []
             st2 = eng2.stats()
-            e2e_states, h2d, d2h = r2.distinct, int(st2.bytes_h2d) + len(cfg), int(st2.bytes_d2h)
+            e2e_states, h2d, d2h = r2.distinct, int(st2.bytes_h2d) + len(cfg), int(st2.bytes_d2h) + C.sizeof(pkg.checker.VsrStats)
+            ok = ok and r2.distinct == EXPECT["distinct"] and r2.rc == 12 and (rank != 0 or len(tr) == EXPECT["violation_level"])
             eng2.close()
         barrier()
         t = torch.tensor([time.time() - te], dtype=torch.float64, device=dev)
         if world > 1:
             tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
         e2e_runs.append(float(t[0]))
-    e2e_s = sorted(e2e_runs)[1]
+    e2e_s = sorted(e2e_runs)[1] if e2e_runs else None
+
+    cfg3 = None
+    if world >= 4 and not args.no_cfg3:
+        try:
+            cfg3 = cfg3_first_violation(pkg, vdist, torch, tdist, group, rank, world, local, dev, barrier)
+        except pkg.VsrError as ex:
+            cfg3 = {"error": str(ex)}
+
+    small_gpu = None
+    if world == 1 and rank == 0:
+        mcs = pkg.ModelChecker.from_constants(SMALL["R"], SMALL["V"], SMALL["L"])
+        ts = time.time()
+        rs = mcs.check(stop_on_violation=False, table_capacity=1 << 22, frontier_capacity=1 << 19)
+        small_gpu = {"value": rs.distinct / (time.time() - ts), "unit": "states/s", "seconds": time.time() - ts, "kernel_seconds": rs.seconds_kernels,
+                     "api": "ModelChecker.check() (engine creation and teardown included)",
+                     "results_match_expected": (rs.distinct, rs.generated, rs.depth) == (SMALL["distinct"], SMALL["generated"], SMALL["depth"])}
 
     if rank == 0:
+        wide = max(range(len(levels_ms[-1])), key=lambda i: levels_ms[-1][i]) if levels_ms and levels_ms[-1] else 0
         out = {
             "metric": "unique states explored/sec (VSR.tla, shipped VSR.cfg constants)", "value": value, "unit": "states/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
@@ -355,48 +437,70 @@ def main():
                                    "reachable set (BASELINE configs[1] = shipped VSR.cfg)",
                        "state_bytes": S, "distinct_states": res.distinct, "states_generated": res.generated, "depth": res.depth,
                        "first_violation_depth": res.violation_level, "parallelism": "fingerprint-sharded x%d" % world,
-                       "l2": "working set (seen-set %.1f GiB) exceeds L2; no flush needed" % (table_cap * 16 / 2**30),
-                       "results_match_expected": bool(ok), "timing": "wall clock bracketed by barrier+synchronize, max over ranks; "
+                       "exchange": "none" if world == 1 else "expand_kernel stores each remote successor into the owner's inbox over NVLink "
+                                   "(CUDA IPC peer mapping, TMA bulk store per destination run); the owner inserts it in its next launch; "
+                                   "C++ level loop, shared-memory all-gather between ranks; NCCL only for the bench's own barrier/timing",
+                       "l2": "working set (seen-set %.1f GiB per GPU) exceeds L2; no flush needed" % (table_cap * 16 / 2**30),
+                       "results_match_expected": bool(ok),
+                       "oracle_coverage": "GPU == CPU oracle as SETS for complete spaces <= 697k states and to a bounded depth of this config "
+                                          "(tests/test_gpu_parity.py); the full-size totals are checked against the numbers every earlier run "
+                                          "and every GPU count reproduced, not against an oracle run (the oracle does 4e5 states/s)",
+                       "timing": "wall clock bracketed by barrier+synchronize, max over ranks; "
                        "device time between CUDA events on the launch stream = %.3f s" % (dev_ms / 1e3)},
             "gpu_launches": launches0,
             "kernel_seconds": kern_s,
-            # N>1: the part of kernel_seconds spent in insert_kernel on records received from peers (slowest rank per level),
-            # and the records rank 0 shipped: what the exchange costs next to the expansion
+            # N>1: the part of kernel_seconds spent in launches that only drain records received from peers (slowest rank per
+            # level), and the records rank 0 pushed to its peers
             "kernel_seconds_insert": insert_ms / 1e3,
             "records_sent_rank0": exchanged,
-            "phase_seconds_rank0_last_step": {k: round(v, 6) for k, v in res.phase_seconds.items()},
-            # rank 0's kernel time per BFS level (ms, expand + insert) in the last timed step, beside the level sizes: where a
-            # multi-GPU run loses against one GPU (narrow levels are launch- and latency-bound, wide ones exchange-bound)
-            "level_ms_rank0_last_step": [round(x, 4) for x in levels_ms[-1]] if levels_ms else [],
+            # the slowest rank's kernel time per BFS level (ms) in the last timed step, beside the level sizes
+            "level_ms_last_step": [round(x, 4) for x in levels_ms[-1]] if levels_ms else [],
             "level_sizes": [int(x) for x in res.level_sizes],
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "traffic_note": "launches differ in size, so no single per-launch figure: the ncu --set full capture of two mid-size "
-                                         "wavefronts (profiles/round1_expand_kernel.md) measured dram read+write = 1.58x the algorithmic bytes",
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
+                         "traffic_note": (traffic.get("note") if traffic else "no ncu capture of this configuration committed yet (profiles/round2_traffic.json)"),
                          "peak_source": peak_src, "bytes_per_state": b_alg, "g": g,
+                         "widest_level": {"depth": wide + 1, "ms": levels_ms[-1][wide] if levels_ms and levels_ms[-1] else None,
+                                          "states_expanded": int(res.level_sizes[wide]) if res.level_sizes else None},
                          "kernel": "expand_kernel<Layout<3,2,3>> (per-GPU states x B_alg / sum of per-level kernel time, max over ranks)"},
-            "e2e": {"value": e2e_states / e2e_s, "unit": "states/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "seconds": e2e_s, "seconds_all_runs": e2e_runs, "api": "ModelChecker.from_cfg_text(cfg).check()" if world == 1 else "dist.GpuEngine + dist.ShardedBfs.run()"},
+            "e2e": ({"value": e2e_states / e2e_s, "unit": "states/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                     "seconds": e2e_s, "seconds_all_runs": e2e_runs,
+                     "api": "ModelChecker.from_cfg_text(cfg).check()" if world == 1 else "ModelChecker.from_cfg_text(cfg) + dist.GpuEngine(group=...).run() + replay_trace()"}
+                    if e2e_s else None),
             "probe_roofline": probe,
             "clocks": clocks,
         }
+        if cfg3 is not None:
+            out["cfg3_first_violation"] = cfg3
+        if small_gpu is not None:
+            out["same_config_small"] = {"workload": "VSR.tla ReplicaCount=3 Values={v1,v2} StartViewOnTimerLimit=1, COMPLETE state space (%d distinct states, depth %d)"
+                                                    % (SMALL["distinct"], SMALL["depth"]), "gpu": small_gpu}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 cores = usable_cores()
-                best_mode, tuned = select_malloc(cores, 1)
                 s = oracle_sample(args.cpu_seconds, cores)
                 s1 = oracle_sample(min(3.0, args.cpu_seconds), 1) if cores > 1 else s
                 out["cpu_baseline"] = {"value": s["rate"], "unit": "states/s", "cores": cores, "kind": "port",
                                        "single_thread_value": s1["rate"],  # the same BFS on one thread for 3 s: how far the all-core figure is from linear
-                                       "sample": "CPU restatement (oracle/, not TLC) BFS of the same config for %.0f s: depth %d, %d distinct states; "
-                                                 "malloc %s (2 s samples: default %.3g, no-trim %.3g states/s)"
-                                                 % (args.cpu_seconds, s["depth"], s["distinct"], "no-trim" if best_mode == "1" else "default",
-                                                    tuned["0"], tuned["1"])}
+                                       "sample": "CPU restatement (oracle/, not TLC) BFS of the same config for %.0f s: depth %d, %d distinct states"
+                                                 % (args.cpu_seconds, s["depth"], s["distinct"])}
+                out["same_config_small"]["cpu"] = small_complete_cpu(cores)
             except Exception as ex:  # the GPU line must not be lost to a failure of the reported CPU leg
                 out["cpu_baseline"] = {"error": repr(ex)}
         print(json.dumps(out))
+    if group is not None:
+        group.close()
     if world > 1:
         tdist.destroy_process_group()
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException as ex:  # every rank's traceback must survive torchrun's summary: print it last, on stderr, and exit non-zero
+        if isinstance(ex, SystemExit) and not ex.code:
+            raise
+        import traceback
+        sys.stderr.write("\n[bench.py] rank %s failed:\n%s\n" % (os.environ.get("RANK", "0"), traceback.format_exc()))
+        sys.stderr.flush()
+        os._exit(1)

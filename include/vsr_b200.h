@@ -48,6 +48,8 @@ typedef struct VsrModelInfo {
     int32_t spec_verified;                              /* 1 if a .tla was given and matched VSR.tla's structure */
     uint64_t spec_hash;                                 /* FNV-1a 64 of the .tla bytes (0 if none) */
     char value_names[VSR_MAX_V][32];                    /* model values of Values, cfg order */
+    int32_t check_deadlock;                             /* CHECK_DEADLOCK in the cfg: 1 TRUE, 0 FALSE, -1 absent (TLC's default: check) */
+    int32_t _pad;
 } VsrModelInfo;
 
 /* ---- loading: TLC's `-config VSR.cfg VSR.tla` (grammar of vsr-revisited/paper/VSR.cfg:1-39).
@@ -102,12 +104,17 @@ typedef struct VsrRunOpts {
     int32_t stop_on_violation;   /* 1: stop at the first violating level (TLC behaviour) */
     int32_t keep_trace;          /* 1: keep (parent, binding) per distinct state so a counterexample can be rebuilt */
     int32_t verbose;
-    uint64_t table_capacity;     /* seen-set slots (power of two; 0 = auto from free memory) */
+    uint64_t table_capacity;     /* seen-set slots (any number, rounded up to 64; 0 = auto from free memory) */
     uint64_t frontier_capacity;  /* states per frontier buffer (0 = auto) */
     uint64_t max_states;         /* stop after the level that crosses this many distinct states (0 = none) */
     double max_seconds;          /* stop after the level that crosses this much time (0 = none) */
     int32_t collect_levels;      /* 1: keep every level's states on the host (tests) */
-    int32_t _reserved[7];
+    int32_t _reserved0;
+    /* frontier spill (BASELINE configs[3], "spill to pinned host DRAM"): each of the two frontier buffers continues, after
+       its frontier_capacity states in HBM, with this many states in pinned host memory mapped into the device; the kernels
+       write and read that part over PCIe / C2C.  0 = no spill: a level that does not fit is a 152. */
+    uint64_t frontier_host_capacity;
+    int32_t _reserved[4];
 } VsrRunOpts;
 
 #define VSR_MAX_LEVELS 512
@@ -128,12 +135,16 @@ typedef struct VsrStats {
     int32_t violation_level;              /* depth of the violating state */
     int32_t trace_len;
     int32_t error_code;                   /* first E_* raised on the device (0 = none) */
-    int32_t _pad;
+    int32_t violation_mask;               /* INVARIANT bits violated by the reported state (0 = none reported) */
     uint64_t violation_id;
     uint64_t table_capacity, frontier_capacity;
     uint64_t bytes_table, bytes_frontier;
     uint64_t bytes_h2d, bytes_d2h;         /* host<->device bytes moved by the engine (inputs, per-level counters, trace reads) */
     double seconds_setup;                 /* engine creation: allocation + clearing the seen-set */
+    uint64_t records_sent, records_received; /* several GPUs: records this rank pushed to / drained from peers */
+    double seconds_insert;                /* several GPUs: part of seconds_kernels spent in drain-only launches */
+    int32_t levels_expanded;              /* frontiers expanded = valid entries of level_generated / level_ms */
+    int32_t _pad;
 } VsrStats;
 
 typedef struct VsrEngine VsrEngine;
@@ -144,22 +155,26 @@ typedef struct VsrEngine VsrEngine;
 int vsr_bfs(const VsrModel* m, const VsrRunOpts* opts, VsrStats* stats, void* trace_out, uint8_t* trace_actions,
             size_t trace_cap);
 
-/* Stepwise engine (what vsr_bfs is made of; the multi-GPU host pumps these around its exchange).
- * rank/world: this engine owns the fingerprints f with owner(f) == rank. */
+/* Stepwise engine (what vsr_bfs and vsr_bfs_sharded are made of).
+ * rank/world: this engine owns the fingerprints f with owner(f) == rank (world = 1, 2, 4 or 8: the high bits of f). */
 int vsr_engine_create(const VsrModel* m, const VsrRunOpts* opts, int rank, int world, VsrEngine** out, char* err,
                       size_t errcap);
 void vsr_engine_destroy(VsrEngine* e);
-/* Set the device buffers for outgoing records (world * cap_records * record_bytes, destination-major)
- * and a device array of `world` uint32 counters.  Caller-owned device memory. */
+/* bytes of one record that travels between ranks or into vsr_engine_insert_records: the packed state, then
+ * { uint64 fingerprint; uint64 parent global id << 12 | candidate index | mult << 56 } */
 int vsr_engine_record_bytes(const VsrEngine* e);
-int vsr_engine_set_send_buffers(VsrEngine* e, void* dev_records, uint64_t cap_records_per_dest, void* dev_counts);
 int vsr_engine_seed_init(VsrEngine* e);                       /* inserts Init if this rank owns it */
-/* expands the current frontier: owned successors go to the seen-set, others to the send buffers */
+/* one launch of the wavefront kernel over the whole current frontier (world = 1: that is the level) */
 int vsr_engine_expand(VsrEngine* e);
-/* same for frontier states [first, first + count) only: lets the host bound the exchange buffers by pumping a wide level
- * in several sub-wavefronts (send counters restart at 0 for every part) */
+/* same for frontier states [first, first + count) only */
 int vsr_engine_expand_part(VsrEngine* e, uint64_t first, uint64_t count);
-/* inserts records received from peers (device pointer) */
+/* world > 1, one step = one launch: expand frontier states [first, first + count) — successors owned here are inserted,
+ * the others are stored into their owners' inboxes (half `parity` of the double buffer) by the kernel itself — then insert
+ * the records the peers stored HERE in the previous step: drain_counts[s] from rank s (NULL = none).  sent_out[d] = records
+ * this launch pushed to rank d (tell rank d: it is its drain_counts[this rank] of the next step).  Returns after the
+ * kernel has completed, i.e. after the pushed records have landed. */
+int vsr_engine_step(VsrEngine* e, uint64_t first, uint64_t count, int parity, const uint32_t* drain_counts, uint32_t* sent_out);
+/* inserts records (device pointer, layout above) as states of the level being generated (Init; tests) */
 int vsr_engine_insert_records(VsrEngine* e, const void* dev_records, uint64_t n);
 /* finishes the level: resolves ties, swaps frontiers; writes this rank's level numbers */
 typedef struct VsrLevelInfo {
@@ -167,13 +182,14 @@ typedef struct VsrLevelInfo {
     int32_t violation, deadlock, error_code, overflow;
     uint64_t violation_id, deadlock_id;
     double ms;        /* kernel time of the level on this rank (expand + insert), CUDA events on the launch stream */
-    double ms_insert; /* of which insert_kernel (records received from peers; 0 on a single rank after Init) */
+    double ms_insert; /* of which launches that only inserted records received from peers */
+    int32_t violation_mask, _pad; /* INVARIANT bits (VsrModelInfo.invariant) violated by some new state of the level */
 } VsrLevelInfo;
 int vsr_engine_finish_level(VsrEngine* e, VsrLevelInfo* out);
 uint64_t vsr_engine_frontier_size(const VsrEngine* e);
 /* copies `n` states of the current frontier starting at `first` to a host buffer */
 int vsr_engine_read_frontier(VsrEngine* e, uint64_t first, uint64_t n, void* host_out);
-/* trace record of a locally owned state id: parent global id (rank << 48 | local id) and candidate index */
+/* trace record of a locally owned state id: parent global id (rank << 40 | local id; 2^44 - 1 = none: Init) and candidate index */
 int vsr_engine_trace_record(VsrEngine* e, uint64_t local_id, uint64_t* parent_out, uint32_t* cand_out);
 int vsr_engine_stats(const VsrEngine* e, VsrStats* out);
 /* membership query: *level_out = BFS depth at which `state` (a canonical packed state) was first seen, 0 if it is not
@@ -186,6 +202,45 @@ const char* vsr_engine_last_error(const VsrEngine* e);
 uint64_t vsr_engine_collected(const VsrEngine* e, int level, void* host_out, uint64_t cap_states);
 /* Rebuild the counterexample ending at local state id (single-rank engines). */
 int vsr_engine_build_trace(VsrEngine* e, uint64_t local_id, void* trace_out, uint8_t* trace_actions, size_t trace_cap);
+
+/* ---- several GPUs of one node (TLC's `-workers` / distributed mode).  One rank per GPU — processes
+ * (torchrun) or threads of one process — fingerprint space split by its high bits.  The ranks coordinate through a
+ * VsrGroup: a block of shared memory with a barrier and an all-gather of one small message per rank (a few per wavefront,
+ * about a microsecond each).  The states do not pass through it: expand_kernel stores a successor owned by a peer straight
+ * into that peer's inbox over NVLink (CUDA IPC mapping / peer access) and the peer inserts it in its next launch. */
+typedef struct VsrGroup VsrGroup;
+#define VSR_GROUP_MSG_BYTES 256
+/* processes: `name` is a POSIX shared-memory name ("/vsr-<job>") every rank of the job passes and nobody else uses; rank 0
+ * creates it, the others wait for it up to timeout_s; the name is unlinked once all have attached */
+int vsr_group_open(const char* name, int rank, int world, double timeout_s, VsrGroup** out, char* err, size_t errcap);
+/* threads of one process: `world` handles on one heap block */
+int vsr_group_open_local(int world, VsrGroup** out_handles);
+void vsr_group_close(VsrGroup* g);
+int vsr_group_barrier(VsrGroup* g);                                  /* 0, or 153 when a rank aborted / timed out */
+int vsr_group_allgather(VsrGroup* g, const void* mine, size_t bytes, void* all_out); /* bytes <= VSR_GROUP_MSG_BYTES */
+void vsr_group_abort(VsrGroup* g);                                   /* make every pending and future wait fail */
+void vsr_group_set_timeout(VsrGroup* g, double seconds);
+int vsr_group_rank(const VsrGroup* g);
+int vsr_group_world(const VsrGroup* g);
+const char* vsr_group_last_error(const VsrGroup* g);
+/* collective over the group: allocate this rank's inbox (2 halves x world segments x inbox_records records; 0 = default
+ * from the frontier capacity) and map every peer's.  153 with a message if peer memory is unavailable. */
+int vsr_engine_attach_group(VsrEngine* e, VsrGroup* g, uint64_t inbox_records);
+/* the same kernels with the outgoing records in a LOCAL staging buffer (world segments of inbox_records records, destination
+ * major) for a host that moves them with its own collective: segment d of *stage_out goes to segment <this rank> of half
+ * `parity` of rank d's *inbox_out (2 halves x world segments).  Used by dist.ShardedBfs (torch.distributed all-to-all). */
+int vsr_engine_attach_staged(VsrEngine* e, uint64_t inbox_records, void** stage_out, void** inbox_out, uint64_t* cap_out);
+int vsr_engine_detach(VsrEngine* e);                                 /* collective when attached to a group */
+uint64_t vsr_engine_default_inbox_records(const VsrEngine* e);
+/* The whole BFS, called by every rank of the group with the same opts; all ranks return the same rc and the same totals
+ * (records_sent / received, bytes_* and kernel_launches are this rank's).  part_states = frontier states per rank and step
+ * (0 = from the inbox size).  On a violation / deadlock trace_cands[0 .. *trace_len) is the candidate chain from Init,
+ * walked across ranks: vsr_replay_candidates turns it into the literal behaviour. */
+int vsr_bfs_sharded(VsrEngine* e, const VsrRunOpts* opts, uint64_t part_states, VsrStats* stats, uint32_t* trace_cands, int* trace_len,
+                    size_t trace_cap);
+/* `vsrmc -gpus N`: the same from ONE process, one thread per GPU (devices opts->device ... + ngpus - 1) */
+int vsr_bfs_multi(const VsrModel* m, const VsrRunOpts* opts, int ngpus, uint64_t inbox_records, uint64_t part_states, VsrStats* stats,
+                  void* trace_out, uint8_t* trace_actions, size_t trace_cap, char* err, size_t errcap);
 
 /* Host replay helper for multi-rank traces: given a chain of candidate indices from Init, re-executes
  * them (canonicalising as the engine does) and writes the literal states. */

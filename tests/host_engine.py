@@ -8,9 +8,9 @@ from types import SimpleNamespace
 
 import torch
 
-HDR = struct.Struct("<QQQII")  # fp, meta, parent gid, cand, mult  (vsr_gpu.cuh RecHdr)
+HDR = struct.Struct("<QQ")  # fp, parent gid << 12 | cand | mult << 56  (vsr_gpu.cuh RecHdr)
 GID_SHIFT = 40
-ROOT_PARENT = (1 << 52) - 1
+ROOT_PARENT = (1 << 44) - 1
 
 
 class HostEngine:
@@ -19,7 +19,7 @@ class HostEngine:
         self.dev = torch.device("cpu")
         self.sb = mc.state_bytes
         self.record_bytes = self.sb + HDR.size
-        self.send_capacity = send_capacity
+        self.inbox_records = send_capacity
         self.check_deadlock = check_deadlock
         lg = world.bit_length() - 1
         self.shift = 64 - lg if world > 1 else 64
@@ -36,6 +36,7 @@ class HostEngine:
         self.next = []
         self.level = 0
         self.out = [[] for _ in range(self.world)]
+        self.inbox = [[b"" for _ in range(self.world)] for _ in range(2)]
         self._li = self._blank()
         self.levels = []
 
@@ -66,7 +67,9 @@ class HostEngine:
         if self.owner(fp) == self.rank:
             self._insert(s, fp, self.mc.aux_key(s), ROOT_PARENT, 0, 1)
 
-    def expand_part(self, first, count):
+    def step(self, first, count, parity, drain_counts):
+        """the engine's step: expand frontier[first : first + count] (own successors inserted, the others queued per
+        destination), then insert what the peers sent in the previous step (the other half of the inbox)"""
         full = self.frontier
         self.frontier = full[first:first + count]
         self.out = [[] for _ in range(self.world)]
@@ -74,6 +77,16 @@ class HostEngine:
             self.expand()
         finally:
             self.frontier = full
+        if drain_counts is not None:
+            rb, sb = self.record_bytes, self.sb
+            for src in range(self.world):
+                raw = self.inbox[(parity ^ 1) & 1][src]
+                for i in range(drain_counts[src]):
+                    r = raw[i * rb:(i + 1) * rb]
+                    fp, tm = HDR.unpack(r[sb:])
+                    assert self.owner(fp) == self.rank
+                    self._insert(r[:sb], fp, self.mc.aux_key(r[:sb]), (tm >> 12) & ROOT_PARENT, tm & 0xFFF, (tm >> 56) & 0xF)
+        return [len(x) for x in self.out]
 
     def expand(self):
         import ctypes as C
@@ -101,7 +114,7 @@ class HostEngine:
                 if o == self.rank:
                     self._insert(t, fp, self.mc.aux_key(t), gid, cands[i], int(mult[i]))
                 else:
-                    self.out[o].append(t + HDR.pack(fp, self.mc.aux_key(t), gid, cands[i], int(mult[i])))
+                    self.out[o].append(t + HDR.pack(fp, (gid << 12) | cands[i] | (int(mult[i]) << 56)))
 
     def _enabled_candidates(self, st):
         """true candidate indices (what trace records store) of the enabled bindings, in vsr_successors order"""
@@ -112,24 +125,12 @@ class HostEngine:
         n = lib.vsr_enabled_candidates(self.mc._h, (C.c_uint8 * self.sb).from_buffer_copy(st), buf, 1024)
         return [int(buf[i]) for i in range(n)]
 
-    def send_counts(self):
-        return torch.tensor([len(x) for x in self.out], dtype=torch.int64)
-
-    def send_slice(self, dest, n):
+    def outgoing(self, dest, n):
         data = b"".join(self.out[dest][:n])
         return torch.frombuffer(bytearray(data), dtype=torch.uint8) if data else torch.empty(0, dtype=torch.uint8)
 
-    def new_recv(self, n):
-        return torch.empty((max(n, 1), self.record_bytes), dtype=torch.uint8)
-
-    def insert(self, recs, n):
-        raw = recs.reshape(-1).numpy().tobytes()
-        rb, sb = self.record_bytes, self.sb
-        for i in range(n):
-            r = raw[i * rb:(i + 1) * rb]
-            fp, aux, parent, cand, mult = HDR.unpack(r[sb:])
-            assert self.owner(fp) == self.rank
-            self._insert(r[:sb], fp, aux, parent, cand, mult)
+    def put_incoming(self, parity, src, data, n):
+        self.inbox[parity & 1][src] = data.reshape(-1).numpy().tobytes()[: n * self.record_bytes]
 
     def finish(self):
         li = self._li

@@ -46,8 +46,8 @@ def test_sharded_result_carries_the_fields_the_bench_line_prints():
     _pkg.load()
     from vsr_tlaplus_b200 import dist as vdist
     r = vdist.ShardedResult()
-    assert set(r.phase_seconds) == {"expand", "exchange", "insert", "finish"}
-    assert r.insert_ms_max == 0.0 and r.exchanged_records == 0 and r.level_sizes == []
+    assert set(r.phase_seconds) == {"expand", "exchange", "finish"}
+    assert r.insert_ms_max == 0.0 and r.exchanged_records == 0 and r.level_sizes == [] and r.level_ms == [] and r.launches == 0
 
 
 def test_level_reduce_on_one_rank_is_the_identity():

@@ -48,6 +48,27 @@ def test_shipped_cfg_and_spec_load_unchanged(pkg):
 
 
 @needs_reference
+def test_an_edited_spec_is_refused_not_verified(pkg, tmp_path, monkeypatch):
+    """Next and the invariants are hand-lowered, so a .tla whose definitions differ from VSR.tla must not load as "verified"
+    (ADVICE round 1): an edited invariant body keeps the module name, the VARIABLES and the disjunct names."""
+    text = open(REF_TLA).read()
+    edited = text.replace("AcknowledgedWriteNotLost ==", "AcknowledgedWriteNotLost == TRUE \\/", 1)
+    assert edited != text
+    p = tmp_path / "VSR.tla"
+    p.write_text(edited)
+    with pytest.raises(pkg.VsrError) as ei:
+        pkg.ModelChecker.from_cfg(REF_CFG, str(p))
+    assert ei.value.rc == 150 and "hand" in str(ei.value)
+    # comments, blank lines, trailing blanks and CRLF line ends are not the spec
+    p.write_text("\n".join(("\\* a comment line\n" + ln + "   \r") if i == 200 else ln + "\r" for i, ln in enumerate(text.split("\n"))) + "\n(* block\n comment *)\n")
+    assert pkg.ModelChecker.from_cfg(REF_CFG, str(p)).info.spec_verified == 1
+    # explicit override: loads, loudly, and is NOT reported as verified
+    p.write_text(edited)
+    monkeypatch.setenv("VSR_B200_ALLOW_EDITED_SPEC", "1")
+    assert pkg.ModelChecker.from_cfg(REF_CFG, str(p)).info.spec_verified == 0
+
+
+@needs_reference
 def test_readme_constants_load(pkg, tmp_path):
     """README.md:13-18: the user edits only the constants"""
     cfg = open(REF_CFG).read().replace("Values = {v1, v2}", "Values = {v1, v2, v3}").replace("StartViewOnTimerLimit = 2", "StartViewOnTimerLimit = 3")

@@ -181,7 +181,7 @@ def test_view_ties_resolve_to_smallest_aux_key(pkg):
             f.aux_svc = aux
             variants.append(mc.pack(f))
         assert len({mc.fingerprint(v) for v in variants}) == 1 and len({mc.aux_key(v) for v in variants}) == 3
-        recs = b"".join(v + struct.pack("<QQQII", mc.fingerprint(v), 0, 0, 100 + i, 1) for i, v in enumerate(variants))
+        recs = b"".join(v + struct.pack("<QQ", mc.fingerprint(v), (0 << 12) | (100 + i) | (1 << 56)) for i, v in enumerate(variants))  # vsr_gpu.cuh RecHdr
         t = torch.frombuffer(bytearray(recs), dtype=torch.uint8).cuda()
         eng.insert(t, 3)
         li = eng.finish()

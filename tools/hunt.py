@@ -5,7 +5,7 @@ TLC `dumpTrace tlc` format, and cross-checks the reference's published 24-state 
 (tests/golden/state_transfer_trace.json) against the explored set: every published state must have been seen at a BFS
 depth <= its position in the published trace.
 
-  torchrun --nproc-per-node 8 tools/hunt.py 3 3 3 --table 1073741824 --frontier 200000000 --send 80000000
+  torchrun --nproc-per-node 8 tools/hunt.py 3 3 3 --table 1073741824 --frontier 200000000
 """
 import argparse
 import base64
@@ -26,8 +26,8 @@ def main():
     ap.add_argument("L", type=int)
     ap.add_argument("--table", type=int, default=0)
     ap.add_argument("--frontier", type=int, default=0)
-    ap.add_argument("--send", type=int, default=1 << 20)
-    ap.add_argument("--part", type=int, default=0, help="frontier states per sub-wavefront and rank")
+    ap.add_argument("--inbox", type=int, default=0, help="records per inbox segment (0 = from --frontier)")
+    ap.add_argument("--part", type=int, default=0, help="frontier states per step and rank (0 = from the inbox size)")
     ap.add_argument("--depth", type=int, default=0)
     ap.add_argument("--seconds", type=float, default=0)
     ap.add_argument("--continue-past", action="store_true")
@@ -47,13 +47,14 @@ def main():
         torch.cuda.set_device(local)
         tdist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
+    group = vdist.Group.from_torch() if world > 1 else None
     mc = pkg.ModelChecker.from_constants(args.R, args.V, args.L)
     t0 = time.time()
     eng = vdist.GpuEngine(mc, rank, world, device=local, table_capacity=args.table, frontier_capacity=args.frontier,
-                          send_capacity=args.send, keep_trace=True)
-    bfs = vdist.ShardedBfs(eng, rank, world, part_states=args.part)
+                          inbox_records=args.inbox, keep_trace=True, group=group)
     t1 = time.time()
-    res = bfs.run(max_depth=args.depth, max_seconds=args.seconds, stop_on_violation=not args.continue_past)
+    res = eng.run(max_depth=args.depth, max_seconds=args.seconds, stop_on_violation=not args.continue_past, part_states=args.part,
+                  verbose=True)
     torch.cuda.synchronize(dev)
     t2 = time.time()
 
@@ -92,6 +93,8 @@ def main():
         with open(os.path.join(args.out, "hunt_%s.json" % tag), "w") as f:
             json.dump(out, f)
     eng.close()
+    if group is not None:
+        group.close()
     if world > 1:
         tdist.destroy_process_group()
 

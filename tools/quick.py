@@ -16,7 +16,7 @@ print(json.dumps(dict(cfg=[R,V,L], rc=res.rc, distinct=res.distinct, generated=r
    wall=time.time()-t0, secs=res.seconds_total, kern=res.seconds_kernels, rate=res.distinct/res.seconds_total, krate=res.distinct/max(res.seconds_kernels,1e-9),
    g=res.generated/max(res.distinct,1), probes_per_gen=res.probe_total/max(res.generated,1), ties=res.h2_ties, coll=res.fp_collisions,
    viol_level=res.violation_level, table=res.table_capacity, frontier=res.frontier_capacity, trace=[a for a,_ in res.trace])))
-n=len(res.level_sizes)
+n=len(res.level_sizes) if not os.environ.get('QUIET') else 0
 for i in range(n):
     print(i+1, res.level_sizes[i], res.level_generated[i], round(res.level_ms[i],3), round(res.level_sizes[i]/max(res.level_ms[i],1e-6)/1e3,2), "M new/s")
 if res.trace and len(sys.argv) > 8:

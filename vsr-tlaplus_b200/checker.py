@@ -86,6 +86,7 @@ class VsrModelInfo(C.Structure):
         ("symmetry", C.c_int32), ("view", C.c_int32), ("invariant", C.c_int32),
         ("state_bytes", C.c_int32), ("state_bits", C.c_int32), ("num_candidates", C.c_int32),
         ("spec_verified", C.c_int32), ("spec_hash", C.c_uint64), ("value_names", (C.c_char * 32) * VSR_MAX_V),
+        ("check_deadlock", C.c_int32), ("_pad", C.c_int32),
     ]
 
 
@@ -94,7 +95,8 @@ class VsrRunOpts(C.Structure):
         ("device", C.c_int32), ("check_deadlock", C.c_int32), ("max_depth", C.c_int32),
         ("stop_on_violation", C.c_int32), ("keep_trace", C.c_int32), ("verbose", C.c_int32),
         ("table_capacity", C.c_uint64), ("frontier_capacity", C.c_uint64), ("max_states", C.c_uint64),
-        ("max_seconds", C.c_double), ("collect_levels", C.c_int32), ("_reserved", C.c_int32 * 7),
+        ("max_seconds", C.c_double), ("collect_levels", C.c_int32), ("_reserved0", C.c_int32),
+        ("frontier_host_capacity", C.c_uint64), ("_reserved", C.c_int32 * 4),
     ]
 
 
@@ -106,10 +108,12 @@ class VsrStats(C.Structure):
         ("level_ms", C.c_double * VSR_MAX_LEVELS),
         ("h2_ties", C.c_uint64), ("fp_collisions", C.c_uint64), ("probe_total", C.c_uint64),
         ("kernel_launches", C.c_uint64), ("seconds_total", C.c_double), ("seconds_kernels", C.c_double),
-        ("violation_level", C.c_int32), ("trace_len", C.c_int32), ("error_code", C.c_int32), ("_pad", C.c_int32),
+        ("violation_level", C.c_int32), ("trace_len", C.c_int32), ("error_code", C.c_int32), ("violation_mask", C.c_int32),
         ("violation_id", C.c_uint64), ("table_capacity", C.c_uint64), ("frontier_capacity", C.c_uint64),
         ("bytes_table", C.c_uint64), ("bytes_frontier", C.c_uint64),
         ("bytes_h2d", C.c_uint64), ("bytes_d2h", C.c_uint64), ("seconds_setup", C.c_double),
+        ("records_sent", C.c_uint64), ("records_received", C.c_uint64), ("seconds_insert", C.c_double),
+        ("levels_expanded", C.c_int32), ("_pad", C.c_int32),
     ]
 
 
@@ -129,7 +133,7 @@ class VsrLevelInfo(C.Structure):
         ("new_states", C.c_uint64), ("generated", C.c_uint64), ("frontier_in", C.c_uint64), ("ties", C.c_uint64),
         ("collisions", C.c_uint64), ("violation", C.c_int32), ("deadlock", C.c_int32), ("error_code", C.c_int32),
         ("overflow", C.c_int32), ("violation_id", C.c_uint64), ("deadlock_id", C.c_uint64), ("ms", C.c_double),
-        ("ms_insert", C.c_double),
+        ("ms_insert", C.c_double), ("violation_mask", C.c_int32), ("_pad", C.c_int32),
     ]
 
 
@@ -138,10 +142,14 @@ EXPORTED_SYMBOLS = [
     "vsr_load", "vsr_load_cfg_text", "vsr_model_create", "vsr_model_free", "vsr_model_info", "vsr_init", "vsr_successors", "vsr_enabled_candidates",
     "vsr_canon", "vsr_fingerprint", "vsr_fingerprint_bytewise", "vsr_aux_key", "vsr_invariant", "vsr_unpack", "vsr_pack", "vsr_state_to_tla",
     "vsr_flat_to_tla", "vsr_action_name", "vsr_action_location", "vsr_bfs", "vsr_engine_create", "vsr_engine_destroy",
-    "vsr_engine_record_bytes", "vsr_engine_set_send_buffers", "vsr_engine_seed_init", "vsr_engine_expand", "vsr_engine_expand_part",
+    "vsr_engine_record_bytes", "vsr_engine_seed_init", "vsr_engine_expand", "vsr_engine_expand_part", "vsr_engine_step",
     "vsr_engine_insert_records", "vsr_engine_finish_level", "vsr_engine_frontier_size", "vsr_engine_read_frontier",
     "vsr_engine_trace_record", "vsr_engine_stats", "vsr_engine_reset", "vsr_engine_lookup", "vsr_engine_last_error", "vsr_engine_collected", "vsr_engine_build_trace",
     "vsr_replay_candidates", "vsr_probe_bench", "vsr_simulate", "vsr_walk", "vsr_version",
+    "vsr_group_open", "vsr_group_open_local", "vsr_group_close", "vsr_group_barrier", "vsr_group_allgather", "vsr_group_abort",
+    "vsr_group_set_timeout", "vsr_group_rank", "vsr_group_world", "vsr_group_last_error",
+    "vsr_engine_attach_group", "vsr_engine_attach_staged", "vsr_engine_detach", "vsr_engine_default_inbox_records",
+    "vsr_bfs_sharded", "vsr_bfs_multi",
 ]
 
 _lib = None
@@ -185,7 +193,26 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.vsr_engine_create.argtypes = [vp, C.POINTER(VsrRunOpts), C.c_int, C.c_int, C.POINTER(vp), cp, C.c_size_t]
     lib.vsr_engine_destroy.argtypes = [vp]
     lib.vsr_engine_record_bytes.argtypes = [vp]
-    lib.vsr_engine_set_send_buffers.argtypes = [vp, vp, u64, vp]
+    lib.vsr_engine_step.argtypes = [vp, u64, u64, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    lib.vsr_group_open.argtypes = [cp, C.c_int, C.c_int, C.c_double, C.POINTER(vp), cp, C.c_size_t]
+    lib.vsr_group_open_local.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.vsr_group_close.argtypes = [vp]
+    lib.vsr_group_barrier.argtypes = [vp]
+    lib.vsr_group_allgather.argtypes = [vp, vp, C.c_size_t, vp]
+    lib.vsr_group_abort.argtypes = [vp]
+    lib.vsr_group_set_timeout.argtypes = [vp, C.c_double]
+    lib.vsr_group_rank.argtypes = [vp]
+    lib.vsr_group_world.argtypes = [vp]
+    lib.vsr_group_last_error.argtypes = [vp]
+    lib.vsr_group_last_error.restype = cp
+    lib.vsr_engine_attach_group.argtypes = [vp, vp, u64]
+    lib.vsr_engine_attach_staged.argtypes = [vp, u64, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]
+    lib.vsr_engine_detach.argtypes = [vp]
+    lib.vsr_engine_default_inbox_records.argtypes = [vp]
+    lib.vsr_engine_default_inbox_records.restype = u64
+    lib.vsr_bfs_sharded.argtypes = [vp, C.POINTER(VsrRunOpts), u64, C.POINTER(VsrStats), C.POINTER(C.c_uint32), C.POINTER(C.c_int), C.c_size_t]
+    lib.vsr_bfs_multi.argtypes = [vp, C.POINTER(VsrRunOpts), C.c_int, u64, u64, C.POINTER(VsrStats), vp, C.POINTER(C.c_uint8), C.c_size_t, cp,
+                                  C.c_size_t]
     lib.vsr_engine_seed_init.argtypes = [vp]
     lib.vsr_engine_expand.argtypes = [vp]
     lib.vsr_engine_expand_part.argtypes = [vp, u64, u64]
@@ -261,6 +288,10 @@ class CheckResult:
     bytes_h2d: int = 0
     bytes_d2h: int = 0
     seconds_setup: float = 0.0
+    violated_invariants: List[str] = field(default_factory=list)  # names of the INVARIANTs the reported state violates
+    records_sent: int = 0        # several GPUs: records this rank pushed to peers / drained from its inbox
+    records_received: int = 0
+    seconds_insert: float = 0.0
     trace: List[Tuple[str, bytes]] = field(default_factory=list)  # (action name, packed state)
     levels: List[bytes] = field(default_factory=list)             # collect_levels: raw states per depth
 
@@ -408,11 +439,14 @@ class ModelChecker:
         return "<<\n" + ",\n".join(parts) + "\n>>"
 
     # -- the BFS (GPU) ----------------------------------------------------------------------------
-    def run_opts(self, deadlock: bool = False, max_depth: int = 0, device: int = 0, table_capacity: int = 0,
+    def run_opts(self, deadlock: Optional[bool] = None, max_depth: int = 0, device: int = 0, table_capacity: int = 0,
                  frontier_capacity: int = 0, keep_trace: bool = True, collect_levels: bool = False, max_states: int = 0,
-                 max_seconds: float = 0.0, stop_on_violation: bool = True, verbose: bool = False) -> VsrRunOpts:
+                 max_seconds: float = 0.0, stop_on_violation: bool = True, verbose: bool = False,
+                 frontier_host_capacity: int = 0) -> VsrRunOpts:
         o = VsrRunOpts()
         o.device = device
+        if deadlock is None:  # CHECK_DEADLOCK of the cfg when it has one; otherwise off (VSR.tla has terminal states)
+            deadlock = int(self.info.check_deadlock) == 1
         o.check_deadlock = int(deadlock)
         o.max_depth = max_depth
         o.stop_on_violation = int(stop_on_violation)
@@ -423,6 +457,7 @@ class ModelChecker:
         o.max_states = max_states
         o.max_seconds = max_seconds
         o.collect_levels = int(collect_levels)
+        o.frontier_host_capacity = frontier_host_capacity
         return o
 
     @staticmethod
@@ -436,7 +471,10 @@ class ModelChecker:
             kernel_launches=int(st.kernel_launches), seconds_total=float(st.seconds_total),
             seconds_kernels=float(st.seconds_kernels), violation_level=int(st.violation_level), error_code=int(st.error_code),
             table_capacity=int(st.table_capacity), frontier_capacity=int(st.frontier_capacity), bytes_h2d=int(st.bytes_h2d),
-            bytes_d2h=int(st.bytes_d2h), seconds_setup=float(st.seconds_setup), trace=trace or [], levels=levels or [])
+            bytes_d2h=int(st.bytes_d2h), seconds_setup=float(st.seconds_setup),
+            violated_invariants=[n for n, b in INVARIANT_BITS.items() if int(st.violation_mask) & b],
+            records_sent=int(st.records_sent), records_received=int(st.records_received), seconds_insert=float(st.seconds_insert),
+            trace=trace or [], levels=levels or [])
 
     def check(self, **kw) -> CheckResult:
         """One-GPU BFS through the single C-ABI call ``vsr_bfs`` (counterexample included)."""
@@ -453,6 +491,31 @@ class ModelChecker:
             raise VsrError(rc, "no usable CUDA device / CUDA failure: the BFS has no CPU fallback")
         raw = bytes(tr)
         sb = self.state_bytes
+        trace = [(ACTION_NAMES[acts[i]], raw[i * sb:(i + 1) * sb]) for i in range(int(st.trace_len))]
+        return self.result_from_stats(st, rc, trace)
+
+    def _trace_from_cands(self, cands, n: int) -> List[Tuple[str, bytes]]:
+        cap = n + 1
+        out = self._buf(cap)
+        acts = (C.c_uint8 * cap)()
+        m = self._lib.vsr_replay_candidates(self._h, cands, n, out, acts, cap)
+        if m < 0:
+            raise VsrError(255, "trace replay failed")
+        raw, sb = bytes(out), self.state_bytes
+        return [(ACTION_NAMES[acts[i]], raw[i * sb:(i + 1) * sb]) for i in range(m)]
+
+    def check_multi(self, gpus: int, inbox_records: int = 0, part_states: int = 0, **kw) -> CheckResult:
+        """The BFS sharded over `gpus` GPUs from THIS process (one thread per GPU): ``vsr_bfs_multi``, what `vsrmc -gpus N` runs."""
+        o = self.run_opts(**kw)
+        st = VsrStats()
+        cap = 512
+        tr = self._buf(cap)
+        acts = (C.c_uint8 * cap)()
+        err = C.create_string_buffer(512)
+        rc = self._lib.vsr_bfs_multi(self._h, C.byref(o), gpus, inbox_records, part_states, C.byref(st), tr, acts, cap, err, len(err))
+        if rc in (151, 153):
+            raise VsrError(rc, err.value.decode() or "no usable CUDA devices: the BFS has no CPU fallback")
+        raw, sb = bytes(tr), self.state_bytes
         trace = [(ACTION_NAMES[acts[i]], raw[i * sb:(i + 1) * sb]) for i in range(int(st.trace_len))]
         return self.result_from_stats(st, rc, trace)
 

@@ -24,8 +24,12 @@ static void usage() {
             "  -fp N                fingerprint polynomial index; only 0 (TLC's Polys[0]) is available\n"
             "  -workers N           accepted for compatibility; the BFS runs on the GPU (likewise -metadir, -checkpoint, -coverage,\n"
             "                       -fpmem, -fpbits, -cleanup, -nowarning, -tool, ...); -recover and -dfid are refused\n"
-            "  -gpu N               CUDA device ordinal (default 0)\n"
+            "  -gpu N               CUDA device ordinal (default 0; with -gpus: the first of N consecutive devices)\n"
+            "  -gpus N              shard the state space over N = 1, 2, 4 or 8 GPUs of this node (by fingerprint; the kernel stores\n"
+            "                       a successor owned by another GPU straight into that GPU's inbox over NVLink)\n"
+            "  -inbox N / -part N   -gpus > 1: records per inbox segment / frontier states per GPU and step (default: from -frontier)\n"
             "  -table N / -frontier N   seen-set slots / states per frontier buffer (default: from free memory)\n"
+            "  -spill N             let each frontier buffer continue with N states in pinned host memory once its HBM part is full\n"
             "  -continue            keep exploring after the first violation\n"
             "  -simulate [-num W] [-seed S]   TLC's simulation mode: W random behaviours of at most -depth (default 100) states\n"
             "  -notrace             do not keep parent records (no counterexample)\n");
@@ -33,7 +37,9 @@ static void usage() {
 
 int main(int argc, char** argv) {
     const char *cfg = nullptr, *tla = nullptr, *dump = nullptr;
-    bool simulate = false;
+    bool simulate = false, deadlock_flag = false;
+    int gpus = 1;
+    unsigned long long inbox_records = 0, part_states = 0;
     unsigned long long sim_walks = 1ull << 22, sim_seed = 1;
     VsrRunOpts o;
     memset(&o, 0, sizeof o);
@@ -44,7 +50,10 @@ int main(int argc, char** argv) {
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         if (a == "-config" && i + 1 < argc) cfg = argv[++i];
-        else if (a == "-deadlock") o.check_deadlock = 0;
+        else if (a == "-deadlock") { o.check_deadlock = 0; deadlock_flag = true; }
+        else if (a == "-gpus" && i + 1 < argc) gpus = atoi(argv[++i]);
+        else if (a == "-inbox" && i + 1 < argc) inbox_records = strtoull(argv[++i], 0, 10);
+        else if (a == "-part" && i + 1 < argc) part_states = strtoull(argv[++i], 0, 10);
         else if (a == "-depth" && i + 1 < argc) o.max_depth = atoi(argv[++i]);
         else if (a == "-dumpTrace" && i + 2 < argc) {
             if (strcmp(argv[i + 1], "tlc") != 0) { fprintf(stderr, "Error: only `-dumpTrace tlc FILE` is supported\n"); return 255; }
@@ -62,6 +71,7 @@ int main(int argc, char** argv) {
         } else if (a == "-gpu" && i + 1 < argc) o.device = atoi(argv[++i]);
         else if (a == "-table" && i + 1 < argc) o.table_capacity = strtoull(argv[++i], 0, 10);
         else if (a == "-frontier" && i + 1 < argc) o.frontier_capacity = strtoull(argv[++i], 0, 10);
+        else if (a == "-spill" && i + 1 < argc) o.frontier_host_capacity = strtoull(argv[++i], 0, 10);
         else if (a == "-continue") o.stop_on_violation = 0;
         else if (a == "-simulate") simulate = true;
         else if (a == "-num" && i + 1 < argc) sim_walks = strtoull(argv[++i], 0, 10);
@@ -82,7 +92,9 @@ int main(int argc, char** argv) {
     printf("Model: ReplicaCount=%d ClientCount=%d |Values|=%d StartViewOnTimerLimit=%d RestartEmptyLimit=%d%s%s; packed state %d bytes (%d bits), %d candidate bindings per state\n",
            info.replica_count, info.client_count, info.value_count, info.start_view_on_timer_limit, info.restart_empty_limit,
            info.view ? " VIEW view" : "", info.symmetry ? " SYMMETRY symmValues" : "", info.state_bytes, info.state_bits, info.num_candidates);
-    if (tla) printf("Spec %s verified as MODULE VSR (hash %016llx)\n", tla, (unsigned long long)info.spec_hash);
+    if (tla && info.spec_verified) printf("Spec %s verified as MODULE VSR (hash %016llx)\n", tla, (unsigned long long)info.spec_hash);
+    else if (tla) printf("Spec %s is NOT the VSR.tla this checker lowers: checking the built-in definitions, not the file's\n", tla);
+    if (!deadlock_flag && info.check_deadlock == 0) o.check_deadlock = 0; /* CHECK_DEADLOCK FALSE in the cfg, as in TLC */
     VsrStats st;
     memset(&st, 0, sizeof st);
     const size_t tcap = 512;
@@ -100,11 +112,23 @@ int main(int argc, char** argv) {
         rc = vsr_simulate(m, &so, &sim, trace.data(), acts.data(), tcap);
         st.trace_len = sim.trace_len;
     } else {
-        printf("Running breadth-first search Model-Checking with fp 0 on GPU %d.\n", o.device);
-        rc = vsr_bfs(m, &o, &st, trace.data(), acts.data(), tcap);
+        if (gpus > 1) printf("Running breadth-first search Model-Checking with fp 0 on GPUs %d..%d (state space sharded by fingerprint).\n", o.device, o.device + gpus - 1);
+        else printf("Running breadth-first search Model-Checking with fp 0 on GPU %d.\n", o.device);
+        err[0] = 0;
+        rc = vsr_bfs_multi(m, &o, gpus, inbox_records, part_states, &st, trace.data(), acts.data(), tcap, err, sizeof err);
+        if (err[0]) fprintf(stderr, "Error: %s\n", err);
     }
     if (rc == VSR_RC_VIOLATION || rc == VSR_RC_DEADLOCK) {
-        if (rc == VSR_RC_VIOLATION) printf("Error: Invariant %s is violated.\n", (info.invariant & 1) ? "AcknowledgedWriteNotLost" : "AcknowledgedWritesExistOnMajority");
+        if (rc == VSR_RC_VIOLATION) {
+            /* which of the configured invariants the reported state violates: evaluated on that state (several may be configured) */
+            int mask = st.violation_mask;
+            if (!mask && st.trace_len > 0) mask = vsr_invariant(m, trace.data() + (size_t)(st.trace_len - 1) * info.state_bytes);
+            static const char* names[4] = {"AcknowledgedWriteNotLost", "AcknowledgedWritesExistOnMajority", "NoLogDivergence", "TestInv"};
+            bool any = false;
+            for (int b = 0; b < 4; b++)
+                if (mask & (1 << b)) { printf("Error: Invariant %s is violated.\n", names[b]); any = true; }
+            if (!any) printf("Error: Invariant is violated.\n");
+        }
         else printf("Error: Deadlock reached.\n");
         printf("Error: The behavior up to this point is:\n");
         std::vector<char> buf(1 << 18);

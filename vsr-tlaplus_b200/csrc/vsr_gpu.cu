@@ -14,8 +14,7 @@
 #include <string>
 #include <vector>
 
-#include "vsr_gpu_thunks.cuh"
-#include "vsr_thunks.h"
+#include "vsr_engine.h"
 
 namespace vsr {
 
@@ -31,78 +30,31 @@ const GpuOps* find_gpu_ops(int R, int V, int K) {
 
 using namespace vsr;
 
-static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
-
-#define CK(call)                                                                                        \
-    do {                                                                                                \
-        cudaError_t _e = (call);                                                                        \
-        if (_e != cudaSuccess) {                                                                        \
-            snprintf(e->last_error, sizeof e->last_error, "%s failed: %s", #call, cudaGetErrorString(_e)); \
-            return VSR_RC_SYSTEM;                                                                       \
-        }                                                                                               \
-    } while (0)
-
-struct VsrEngine {
-    const VsrModel* m = nullptr;
-    const GpuOps* g = nullptr;
-    VsrRunOpts opts;
-    int rank = 0, world = 1, owner_shift = 64;
-    int device = 0, sms = 0, blocks_per_sm = 1;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    /* device memory */
-    uint64_t* table = nullptr;
-    uint64_t table_cap = 0;
-    uint32_t* frontier[2] = {nullptr, nullptr};
-    uint64_t frontier_cap = 0;
-    uint64_t* trace = nullptr;
-    uint64_t trace_cap = 0;
-    DevCounters* ctr = nullptr;
-    uint8_t* ties = nullptr;
-    uint64_t tie_cap = 0;
-    uint64_t* fp_tab = nullptr;
-    uint8_t* send = nullptr;
-    uint64_t send_cap = 0;
-    unsigned int* send_count = nullptr;
-    uint64_t* sent_cache = nullptr;
-    uint64_t sent_cap = 0;
-    uint8_t* init_rec = nullptr;
-    /* BFS position */
-    int cur = 0;                 /* which frontier buffer is the current level */
-    uint64_t n_cur = 0;          /* states in it */
-    uint64_t cur_base = 0;       /* local id of its first state */
-    uint64_t next_base = 0;      /* local id the next level starts at */
-    int level = 0;               /* depth of the current frontier (Init = 1) */
-    bool level_open = false;     /* counters reset for the level being generated */
-    VsrStats st;
-    double level_ms_acc = 0;
-    double level_ms_insert_acc = 0; /* the part of level_ms_acc spent in insert_kernel (records from peers) */
-    std::vector<std::vector<uint8_t>> collected; /* per level states (collect_levels) */
-    char last_error[256] = {0};
-};
-
-static int engine_reset_level(VsrEngine* e) {
+int engine_reset_level(VsrEngine* e) {
     CK(cudaMemsetAsync(e->ctr, 0, sizeof(DevCounters), e->stream));
     static const unsigned long long ones = ~0ull;
     CK(cudaMemcpyAsync(&e->ctr->viol_id, &ones, 8, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(&e->ctr->dead_id, &ones, 8, cudaMemcpyHostToDevice, e->stream));
-    if (e->send_count) CK(cudaMemsetAsync(e->send_count, 0, sizeof(unsigned int) * e->world, e->stream));
     e->level_open = true;
     e->level_ms_acc = 0;
     e->level_ms_insert_acc = 0;
     return 0;
 }
 
-static void fill_params(VsrEngine* e, ExpandParams& p) {
+void fill_params(VsrEngine* e, ExpandParams& p) {
     memset(&p, 0, sizeof p);
     p.in = e->frontier[e->cur];
     p.n_in = e->n_cur;
     p.in_base = e->cur_base;
+    p.in_hi = e->frontier_host[e->cur];
+    p.in_split = e->frontier_host_cap ? e->frontier_cap : ~0ull;
     p.out = e->frontier[e->cur ^ 1];
-    p.out_cap = e->frontier_cap;
+    p.out_hi = e->frontier_host[e->cur ^ 1];
+    p.out_split = e->frontier_host_cap ? e->frontier_cap : ~0ull;
+    p.out_cap = e->frontier_cap + e->frontier_host_cap;
     p.out_base = e->next_base;
     p.table = e->table;
-    p.table_mask = e->table_cap - 1;
+    p.table_cap = e->table_cap;
     p.trace = e->trace;
     p.trace_cap = e->trace_cap;
     p.ctr = e->ctr;
@@ -115,11 +67,8 @@ static void fill_params(VsrEngine* e, ExpandParams& p) {
     p.rank = e->rank;
     p.world = e->world;
     p.owner_shift = e->owner_shift;
-    p.send = e->send;
-    p.send_cap = e->send_cap;
     p.send_count = e->send_count;
-    p.sent_cache = e->sent_cache;
-    p.sent_mask = e->sent_cap ? e->sent_cap - 1 : 0;
+    p.push_cap = e->inbox_cap;
 }
 
 extern "C" {
@@ -131,7 +80,8 @@ int vsr_engine_create(const VsrModel* m, const VsrRunOpts* opts, int rank, int w
     };
     if (!m || !opts || !out) return fail(VSR_RC_ERROR, "null argument");
     if (!m->gpu) return fail(VSR_RC_CONFIG_ERROR, "no GPU kernels compiled for this configuration");
-    if (world < 1 || (world & (world - 1)) || rank < 0 || rank >= world) return fail(VSR_RC_CONFIG_ERROR, "world must be a power of two and 0 <= rank < world");
+    if (world < 1 || world > MAX_WORLD || (world & (world - 1)) || rank < 0 || rank >= world)
+        return fail(VSR_RC_CONFIG_ERROR, "world must be 1, 2, 4 or 8 and 0 <= rank < world");
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
     if (ce != cudaSuccess || ndev == 0)
@@ -174,11 +124,8 @@ int vsr_engine_create(const VsrModel* m, const VsrRunOpts* opts, int rank, int w
     cudaMemGetInfo(&free_b, &total_b);
     uint64_t tcap = opts->table_capacity, fcap = opts->frontier_capacity;
     const uint64_t S = (uint64_t)e->g->bytes;
-    if (!tcap) { /* table 16 B/slot + trace 8 B per state at load <= 7/8  ->  23 B per slot; give it ~45% of free memory */
-        tcap = 1;
-        while (tcap * 2 * 23 <= (uint64_t)(free_b * 0.45)) tcap *= 2;
-    }
-    if (tcap & (tcap - 1)) { uint64_t p2 = 1; while (p2 < tcap) p2 *= 2; tcap = p2; }
+    if (!tcap) tcap = (uint64_t)(free_b * 0.45) / 23; /* table 16 B/slot + trace 8 B per state at load <= 7/8  ->  23 B per slot; ~45% of free memory */
+    tcap = (tcap + 63) & ~63ull; /* any size (whole buckets / cache lines), not only powers of two */
     if (!fcap) fcap = (uint64_t)(free_b * 0.40) / (2 * S);
     if (fcap < 64) fcap = 64;
     e->table_cap = tcap;
@@ -189,24 +136,21 @@ int vsr_engine_create(const VsrModel* m, const VsrRunOpts* opts, int rank, int w
     if ((ce = cudaMemsetAsync(e->table, 0, tcap * 16, e->stream)) != cudaSuccess) return bail("memset", ce);
     for (int i = 0; i < 2; i++)
         if ((ce = cudaMallocAsync((void**)&e->frontier[i], fcap * S, e->stream)) != cudaSuccess) return bail("cudaMalloc(frontier)", ce);
+    if (opts->frontier_host_capacity) { /* spill: each frontier buffer continues in pinned, device-mapped host memory */
+        e->frontier_host_cap = opts->frontier_host_capacity;
+        for (int i = 0; i < 2; i++)
+            if ((ce = cudaHostAlloc((void**)&e->frontier_host[i], e->frontier_host_cap * S, cudaHostAllocPortable | cudaHostAllocMapped)) != cudaSuccess)
+                return bail("cudaHostAlloc(frontier spill)", ce);
+    }
     if (e->trace_cap && (ce = cudaMallocAsync((void**)&e->trace, e->trace_cap * 8, e->stream)) != cudaSuccess) return bail("cudaMalloc(trace)", ce);
     if ((ce = cudaMallocAsync((void**)&e->ctr, sizeof(DevCounters), e->stream)) != cudaSuccess) return bail("cudaMalloc", ce);
     if ((ce = cudaMallocAsync((void**)&e->ties, e->tie_cap * (size_t)e->g->tie_bytes, e->stream)) != cudaSuccess) return bail("cudaMalloc", ce);
     if ((ce = cudaMallocAsync((void**)&e->fp_tab, 8 * 256 * 8, e->stream)) != cudaSuccess) return bail("cudaMalloc", ce);
-    if (world > 1) { /* sender-side duplicate filter: 1/8 of the seen-set's slots, 8 B each */
-        uint64_t div = 8; /* tuning hook VSR_SENT_FILTER_DIV = 1, 2, 4 ... 64: a larger filter ships fewer duplicates (memory permitting) */
-        if (const char* s = getenv("VSR_SENT_FILTER_DIV")) {
-            const long d = strtol(s, nullptr, 10);
-            if (d >= 1 && d <= 64 && (d & (d - 1)) == 0) div = (uint64_t)d;
-        }
-        e->sent_cap = tcap / div < (1ull << 16) ? (1ull << 16) : tcap / div;
-        if ((ce = cudaMallocAsync((void**)&e->sent_cache, e->sent_cap * 8, e->stream)) != cudaSuccess) return bail("cudaMalloc(sent filter)", ce);
-        if ((ce = cudaMemsetAsync(e->sent_cache, 0, e->sent_cap * 8, e->stream)) != cudaSuccess) return bail("memset", ce);
-    }
+    if (world > 1 && (ce = cudaMallocAsync((void**)&e->send_count, sizeof(unsigned int) * MAX_WORLD, e->stream)) != cudaSuccess) return bail("cudaMalloc", ce);
     if ((ce = cudaMallocAsync((void**)&e->init_rec, e->g->rec_bytes, e->stream)) != cudaSuccess) return bail("cudaMalloc", ce);
     if ((ce = cudaMemcpyAsync(e->fp_tab, fp64_table(), 8 * 256 * 8, cudaMemcpyHostToDevice, e->stream)) != cudaSuccess) return bail("memcpy", ce);
     e->st.table_capacity = tcap;
-    e->st.frontier_capacity = fcap;
+    e->st.frontier_capacity = fcap + e->frontier_host_cap;
     e->st.bytes_table = tcap * 16;
     e->st.bytes_frontier = 2 * fcap * S;
     e->st.bytes_h2d += 8 * 256 * 8;
@@ -220,12 +164,15 @@ void vsr_engine_destroy(VsrEngine* e) {
     if (e->stream) cudaFreeAsync(e->table, e->stream); else cudaFree(e->table);
     if (e->stream) cudaFreeAsync(e->frontier[0], e->stream); else cudaFree(e->frontier[0]);
     if (e->stream) cudaFreeAsync(e->frontier[1], e->stream); else cudaFree(e->frontier[1]);
+    for (int i = 0; i < 2; i++)
+        if (e->frontier_host[i]) cudaFreeHost(e->frontier_host[i]);
     if (e->stream) cudaFreeAsync(e->trace, e->stream); else cudaFree(e->trace);
     if (e->stream) cudaFreeAsync(e->ctr, e->stream); else cudaFree(e->ctr);
     if (e->stream) cudaFreeAsync(e->ties, e->stream); else cudaFree(e->ties);
     if (e->stream) cudaFreeAsync(e->fp_tab, e->stream); else cudaFree(e->fp_tab);
     if (e->stream) cudaFreeAsync(e->init_rec, e->stream); else cudaFree(e->init_rec);
-    if (e->stream) cudaFreeAsync(e->sent_cache, e->stream); else cudaFree(e->sent_cache);
+    if (e->stream) cudaFreeAsync(e->send_count, e->stream); else cudaFree(e->send_count);
+    vsr_engine_detach(e);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->stream) { cudaStreamSynchronize(e->stream); cudaStreamDestroy(e->stream); }
@@ -233,13 +180,6 @@ void vsr_engine_destroy(VsrEngine* e) {
 }
 
 int vsr_engine_record_bytes(const VsrEngine* e) { return e->g->rec_bytes; }
-
-int vsr_engine_set_send_buffers(VsrEngine* e, void* dev_records, uint64_t cap_records_per_dest, void* dev_counts) {
-    e->send = (uint8_t*)dev_records;
-    e->send_cap = cap_records_per_dest;
-    e->send_count = (unsigned int*)dev_counts;
-    return 0;
-}
 
 /* Level 1: the single initial state (VSR.tla:323-348), inserted by the rank that owns its fingerprint.
    The "current frontier" is empty and the "next" frontier receives Init; finish_level() then advances. */
@@ -259,10 +199,7 @@ int vsr_engine_seed_init(VsrEngine* e) {
     if (owner != e->rank) return 0;
     RecHdr* h = (RecHdr*)(rec.data() + e->g->bytes);
     h->fp = fp;
-    h->meta = 0; /* 0 = "compute on device" (insert_kernel) */
-    h->parent = ~0ull >> 12;
-    h->cand = 0;
-    h->mult = 1;
+    h->tm = make_trec(ROOT_GID, 0) | (1ull << 56); /* no parent; stands for one generated state */
     CK(cudaMemcpyAsync(e->init_rec, rec.data(), rec.size(), cudaMemcpyHostToDevice, e->stream));
     e->st.bytes_h2d += rec.size();
     InsertParams q;
@@ -275,26 +212,56 @@ int vsr_engine_seed_init(VsrEngine* e) {
     return 0;
 }
 
-/* expand frontier states [first, first + count) of the current level (count = 0: nothing to do on this rank) */
-int vsr_engine_expand_part(VsrEngine* e, uint64_t first, uint64_t count) {
+/* One launch of the wavefront kernel: expand frontier states [first, first + count) of the current level (count = 0:
+   nothing to expand on this rank) — successors this rank owns are inserted, the others are pushed into their owners'
+   inboxes, half `parity` — and then insert the records peers pushed HERE in the previous step (the other half):
+   drain_counts[s] records from rank s (NULL = none).  sent_out[d] = records pushed to rank d by this launch. */
+int vsr_engine_step(VsrEngine* e, uint64_t first, uint64_t count, int parity, const uint32_t* drain_counts, uint32_t* sent_out) {
     if (!e->level_open) {
         int rc = engine_reset_level(e);
         if (rc) return rc;
     }
-    if (e->send_count) CK(cudaMemsetAsync(e->send_count, 0, sizeof(unsigned int) * e->world, e->stream));
     if (first >= e->n_cur) count = 0;
     if (first + count > e->n_cur) count = e->n_cur - first;
-    if (count == 0) {
-        CK(cudaStreamSynchronize(e->stream));
-        return 0;
-    }
     ExpandParams p;
     fill_params(e, p);
-    p.in += first * (uint64_t)e->g->nw;
+    if (first < p.in_split || !e->frontier_host_cap) {
+        p.in += first * (uint64_t)e->g->nw;
+        if (e->frontier_host_cap) p.in_split -= first;
+    } else { /* this part lies entirely in the host part of the frontier */
+        p.in = p.in_hi + (first - p.in_split) * (uint64_t)e->g->nw;
+        p.in_hi = nullptr;
+        p.in_split = ~0ull;
+    }
     p.n_in = count;
     p.in_base += first;
+    uint64_t drain_total = 0;
+    if (e->world > 1) {
+        if (!e->inbox) {
+            snprintf(e->last_error, sizeof e->last_error, "world > 1 without an exchange: call vsr_engine_attach_group or vsr_engine_attach_staged first");
+            return VSR_RC_ERROR;
+        }
+        const uint64_t seg = e->inbox_cap * (uint64_t)e->g->rec_bytes;
+        parity &= 1;
+        for (int r = 0; r < e->world; r++) {
+            p.push[r] = e->stage ? e->stage + (uint64_t)r * seg : (e->peer_inbox[r] ? e->peer_inbox[r] + ((uint64_t)parity * e->world + e->rank) * seg : nullptr);
+            p.drain[r] = e->inbox + ((uint64_t)(parity ^ 1) * e->world + r) * seg;
+            uint32_t n = (drain_counts && r != e->rank) ? drain_counts[r] : 0;
+            if (n > e->inbox_cap) n = (uint32_t)e->inbox_cap; /* the sender reported the overflow; never read past the segment */
+            p.drain_n[r] = n;
+            drain_total += n;
+        }
+        p.drain_total = drain_total;
+        CK(cudaMemsetAsync(e->send_count, 0, sizeof(unsigned int) * MAX_WORLD, e->stream));
+    }
+    if (sent_out) memset(sent_out, 0, sizeof(uint32_t) * e->world);
+    if (count == 0 && drain_total == 0) return 0;
     CK(cudaMemsetAsync(&e->ctr->work_next, 0, sizeof(unsigned long long), e->stream));
-    const uint64_t want_blocks = (count + e->g->states_per_block - 1) / e->g->states_per_block;
+    CK(cudaMemsetAsync(&e->ctr->drain_next, 0, sizeof(unsigned long long), e->stream));
+    const uint64_t spb = (uint64_t)e->g->states_per_block;
+    uint64_t want_blocks = (count + spb - 1) / spb;
+    const uint64_t drain_blocks = (drain_total + spb - 1) / spb;
+    if (drain_blocks > want_blocks) want_blocks = drain_blocks;
     const uint64_t max_blocks = (uint64_t)e->sms * e->blocks_per_sm; /* persistent: whole multiples of the SM count */
     int grid = (int)(want_blocks < max_blocks ? want_blocks : max_blocks);
     if (grid < 1) grid = 1;
@@ -302,14 +269,24 @@ int vsr_engine_expand_part(VsrEngine* e, uint64_t first, uint64_t count) {
     CK(e->g->launch_expand(p, grid, e->stream));
     CK(cudaEventRecord(e->ev1, e->stream));
     e->st.kernel_launches++;
-    CK(cudaEventSynchronize(e->ev1));
+    if (e->world > 1 && sent_out) {
+        CK(cudaMemcpyAsync(sent_out, e->send_count, sizeof(uint32_t) * e->world, cudaMemcpyDeviceToHost, e->stream));
+        e->st.bytes_d2h += sizeof(uint32_t) * e->world;
+    }
+    CK(cudaStreamSynchronize(e->stream)); /* the pushed records have landed (kernel completion) before the host tells anybody */
     float ms = 0;
     cudaEventElapsedTime(&ms, e->ev0, e->ev1);
     e->level_ms_acc += ms;
+    if (count == 0) e->level_ms_insert_acc += ms;
+    if (sent_out)
+        for (int r = 0; r < e->world; r++) e->records_sent += sent_out[r];
+    e->records_received += drain_total;
     return 0;
 }
 
-int vsr_engine_expand(VsrEngine* e) { return vsr_engine_expand_part(e, 0, e->n_cur); }
+int vsr_engine_expand_part(VsrEngine* e, uint64_t first, uint64_t count) { return vsr_engine_step(e, first, count, 0, nullptr, nullptr); }
+
+int vsr_engine_expand(VsrEngine* e) { return vsr_engine_step(e, 0, e->n_cur, 0, nullptr, nullptr); }
 
 int vsr_engine_insert_records(VsrEngine* e, const void* dev_records, uint64_t n) {
     if (!e->level_open) {
@@ -338,13 +315,15 @@ int vsr_engine_finish_level(VsrEngine* e, VsrLevelInfo* out) {
     CK(cudaMemcpyAsync(&c, e->ctr, sizeof c, cudaMemcpyDeviceToHost, e->stream));
     e->st.bytes_d2h += sizeof c;
     CK(cudaStreamSynchronize(e->stream));
-    if (c.tie_count > 0 && c.tie_count <= e->tie_cap && !c.overflow && c.out_count <= e->frontier_cap) {
+    const uint64_t fcap_total = e->frontier_cap + e->frontier_host_cap;
+    if (c.tie_count > 0 && c.tie_count <= e->tie_cap && !c.overflow && c.out_count <= fcap_total) {
         /* same-level states with equal VIEW but different aux variables.  Keep, per fingerprint, the
            smallest (aux_key, parent, candidate) among the late arrivals, sorted by fingerprint, and let the patch
            kernel replace first arrivals that lose; the level's violation verdict is recomputed from scratch. */
         const size_t tb = (size_t)e->g->tie_bytes;
         std::vector<uint8_t> host(c.tie_count * tb);
-        CK(cudaMemcpy(host.data(), e->ties, host.size(), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpyAsync(host.data(), e->ties, host.size(), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
         std::vector<const uint8_t*> recs;
         for (uint64_t i = 0; i < c.tie_count; i++) recs.push_back(host.data() + i * tb);
         auto key = [](const uint8_t* r) { return (const TieRec*)r; };
@@ -363,10 +342,12 @@ int vsr_engine_finish_level(VsrEngine* e, VsrLevelInfo* out) {
             best.insert(best.end(), recs[i], recs[i] + tb);
             nbest++;
         }
-        CK(cudaMemcpy(e->ties, best.data(), best.size(), cudaMemcpyHostToDevice));
+        /* everything on the engine's stream (it does not synchronise with the legacy stream); `best` and `ones` outlive
+           the copies: the stream is synchronised below before they go out of scope */
+        CK(cudaMemcpyAsync(e->ties, best.data(), best.size(), cudaMemcpyHostToDevice, e->stream));
         static const unsigned long long ones = ~0ull;
-        CK(cudaMemcpy(&e->ctr->viol_id, &ones, 8, cudaMemcpyHostToDevice));
-        CK(cudaMemset(&e->ctr->viol_which, 0, sizeof(int)));
+        CK(cudaMemcpyAsync(&e->ctr->viol_id, &ones, 8, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemsetAsync(&e->ctr->viol_which, 0, sizeof(int), e->stream));
         ExpandParams p;
         fill_params(e, p);
         CK(e->g->launch_patch(p, e->ties, nbest, c.out_count, e->stream));
@@ -385,6 +366,7 @@ int vsr_engine_finish_level(VsrEngine* e, VsrLevelInfo* out) {
     li.collisions = c.collisions;
     li.violation = c.viol_id != ~0ull;
     li.violation_id = c.viol_id;
+    li.violation_mask = c.viol_which;
     li.deadlock = c.dead_id != ~0ull;
     li.deadlock_id = c.dead_id;
     li.error_code = c.error;
@@ -394,7 +376,7 @@ int vsr_engine_finish_level(VsrEngine* e, VsrLevelInfo* out) {
     if (c.overflow) {
         snprintf(e->last_error, sizeof e->last_error, "capacity exceeded (%s): %llu new states this level, frontier capacity %llu",
                  c.overflow == 1 ? "frontier" : (c.overflow == 2 ? "tie list" : (c.overflow == 3 ? "send buffer" : "seen-set")), (unsigned long long)c.out_count,
-                 (unsigned long long)e->frontier_cap);
+                 (unsigned long long)fcap_total);
     }
     if (!li.overflow && e->st.distinct + c.out_count > e->table_cap - e->table_cap / 8) {
         li.overflow = 4; /* seen-set load above 7/8: probe chains explode long before it is literally full */
@@ -402,7 +384,7 @@ int vsr_engine_finish_level(VsrEngine* e, VsrLevelInfo* out) {
                  (unsigned long long)(e->st.distinct + c.out_count), (unsigned long long)e->table_cap);
     }
     /* advance */
-    const uint64_t n_new = c.out_count <= e->frontier_cap ? c.out_count : e->frontier_cap;
+    const uint64_t n_new = c.out_count <= fcap_total ? c.out_count : fcap_total;
     e->st.generated += c.generated;
     e->st.distinct += n_new;
     e->st.h2_ties += c.ties;
@@ -414,6 +396,7 @@ int vsr_engine_finish_level(VsrEngine* e, VsrLevelInfo* out) {
     if (e->level >= 1 && e->level - 1 < VSR_MAX_LEVELS) {
         e->st.level_generated[e->level - 1] = c.generated;
         e->st.level_ms[e->level - 1] = e->level_ms_acc;
+        e->st.levels_expanded = e->level;
     }
     if (n_new > 0 && gen_level - 1 < VSR_MAX_LEVELS) {
         e->st.level_sizes[gen_level - 1] = n_new;
@@ -431,7 +414,7 @@ int vsr_engine_finish_level(VsrEngine* e, VsrLevelInfo* out) {
     e->level_open = false;
     if (e->opts.collect_levels && n_new) {
         std::vector<uint8_t> host((size_t)n_new * e->g->bytes);
-        CK(cudaMemcpy(host.data(), e->frontier[e->cur], host.size(), cudaMemcpyDeviceToHost));
+        if (vsr_engine_read_frontier(e, 0, n_new, host.data())) return VSR_RC_SYSTEM;
         e->collected.push_back(std::move(host));
     }
     if (out) *out = li;
@@ -442,7 +425,10 @@ uint64_t vsr_engine_frontier_size(const VsrEngine* e) { return e->n_cur; }
 
 int vsr_engine_read_frontier(VsrEngine* e, uint64_t first, uint64_t n, void* host_out) {
     if (first + n > e->n_cur) return VSR_RC_ERROR;
-    CK(cudaMemcpy(host_out, (const uint8_t*)e->frontier[e->cur] + first * e->g->bytes, n * e->g->bytes, cudaMemcpyDeviceToHost));
+    const uint64_t S = (uint64_t)e->g->bytes;
+    const uint64_t in_dev = first < e->frontier_cap ? std::min(n, e->frontier_cap - first) : 0; /* the rest is in the host part (spill) */
+    if (in_dev) CK(cudaMemcpy(host_out, (const uint8_t*)e->frontier[e->cur] + first * S, in_dev * S, cudaMemcpyDeviceToHost));
+    if (n > in_dev) memcpy((uint8_t*)host_out + in_dev * S, (const uint8_t*)e->frontier_host[e->cur] + (first + in_dev - e->frontier_cap) * S, (n - in_dev) * S);
     return 0;
 }
 
@@ -451,7 +437,7 @@ int vsr_engine_trace_record(VsrEngine* e, uint64_t local_id, uint64_t* parent_ou
     uint64_t t = 0;
     CK(cudaMemcpy(&t, e->trace + local_id, 8, cudaMemcpyDeviceToHost));
     e->st.bytes_d2h += 8;
-    *parent_out = t >> 12;
+    *parent_out = (t >> 12) & GID_MASK;
     *cand_out = (uint32_t)(t & 0xFFF);
     return 0;
 }
@@ -466,7 +452,7 @@ int vsr_engine_lookup(VsrEngine* e, const void* state, int* level_out, int* owne
     if (owner != e->rank) return 0;
     const uint32_t chk = e->g->check_hash((const uint32_t*)state, e->m->run.use_view);
     unsigned long long* d = (unsigned long long*)&e->ctr->work_next; /* scratch word; counters are reset per level */
-    lookup_kernel<<<1, 1, 0, e->stream>>>(e->table, e->table_cap - 1, fp, chk, d);
+    lookup_kernel<<<1, 1, 0, e->stream>>>(e->table, e->table_cap, fp, chk, d);
     CK(cudaGetLastError());
     unsigned long long meta = 0;
     CK(cudaMemcpyAsync(&meta, d, 8, cudaMemcpyDeviceToHost, e->stream));
@@ -477,11 +463,11 @@ int vsr_engine_lookup(VsrEngine* e, const void* state, int* level_out, int* owne
 
 int vsr_engine_reset(VsrEngine* e) {
     CK(cudaMemsetAsync(e->table, 0, e->table_cap * 16, e->stream));
-    if (e->sent_cache) CK(cudaMemsetAsync(e->sent_cache, 0, e->sent_cap * 8, e->stream));
     const uint64_t tc = e->st.table_capacity, fc = e->st.frontier_capacity, bt = e->st.bytes_table, bf = e->st.bytes_frontier;
     memset(&e->st, 0, sizeof e->st);
     e->st.table_capacity = tc; e->st.frontier_capacity = fc; e->st.bytes_table = bt; e->st.bytes_frontier = bf;
     e->cur = 0; e->n_cur = 0; e->cur_base = 0; e->next_base = 0; e->level = 0; e->level_open = false;
+    e->records_sent = e->records_received = 0;
     e->collected.clear();
     return 0;
 }
@@ -506,7 +492,7 @@ int vsr_engine_build_trace(VsrEngine* e, uint64_t local_id, void* trace_out, uin
     if (e->world != 1) return -VSR_RC_ERROR; /* multi-rank chains are walked by the host that owns the collectives */
     std::vector<uint32_t> cands;
     uint64_t id = local_id;
-    const uint64_t root_parent = (~0ull >> 12) & ((1ull << 52) - 1);
+    const uint64_t root_parent = ROOT_GID;
     for (int guard = 0; guard < 100000; guard++) {
         uint64_t parent;
         uint32_t cand;
@@ -565,6 +551,8 @@ int vsr_bfs(const VsrModel* m, const VsrRunOpts* opts, VsrStats* stats, void* tr
     if (bad_id != ~0ull && trace_out && e->trace) {
         int n = vsr_engine_build_trace(e, bad_id, trace_out, trace_actions, trace_cap);
         s.trace_len = n > 0 ? n : 0;
+        if (n > 0 && result == VSR_RC_VIOLATION)
+            s.violation_mask = m->ops->invariant(&m->run, (const uint32_t*)((const uint8_t*)trace_out + (size_t)(n - 1) * m->ops->bytes));
     }
     s.seconds_total = now_s() - t0;
     s.seconds_setup = t_setup;
@@ -660,7 +648,7 @@ int vsr_simulate(const VsrModel* m, const VsrSimOpts* o, VsrSimStats* out, void*
 int vsr_probe_bench(int device, uint64_t capacity, uint64_t n, double dup_frac, int iters, double* ms_out) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return VSR_RC_SYSTEM;
-    if (capacity & (capacity - 1)) return VSR_RC_ERROR;
+    if (capacity < 64 || (capacity & 63)) return VSR_RC_ERROR;
     cudaSetDevice(device);
     uint64_t* table = nullptr;
     unsigned long long* cnt = nullptr;
@@ -678,7 +666,7 @@ int vsr_probe_bench(int device, uint64_t capacity, uint64_t n, double dup_frac, 
         cudaMemset(table, 0, capacity * 16);
         cudaMemset(cnt, 0, 16);
         cudaEventRecord(a);
-        probe_bench_kernel<<<prop.multiProcessorCount * 8, 256>>>(table, capacity - 1, n, distinct, 1 + it, cnt, cnt + 1);
+        probe_bench_kernel<<<prop.multiProcessorCount * 8, 256>>>(table, capacity, n, distinct, 1 + it, cnt, cnt + 1);
         cudaEventRecord(b);
         if (cudaEventSynchronize(b) != cudaSuccess) { cudaFree(table); cudaFree(cnt); return VSR_RC_SYSTEM; }
         float ms = 0;

@@ -43,6 +43,7 @@ struct DevCounters {
     unsigned long long dead_id;     /* smallest global id of an expanded state without successors */
     unsigned long long work_next;   /* next 32-state chunk to hand out */
     unsigned long long tie_count;   /* entries in the tie list */
+    unsigned long long drain_next;  /* next chunk of inbox records to hand out */
     int error;                      /* first E_* raised */
     int overflow;                   /* next frontier / send buffer / tie list full */
     int viol_which;                 /* mask bit of the violated invariant */
@@ -56,23 +57,30 @@ struct TieRec {
     uint32_t auxkey, cand, check, _pad;
 };
 
-/* record shipped to the owner rank of a successor: state words, then this header */
+/* record shipped to the owner rank of a successor: the state's words, then this 16-byte header.  The owner recomputes the
+   check hash and the aux key from the words (a few dozen instructions); the 64-bit fingerprint travels because computing
+   it is the expensive part and the sender needs it anyway to find the owner. */
 struct RecHdr {
     uint64_t fp;
-    uint64_t meta;
-    uint64_t parent; /* global id: rank << 40 | local id */
-    uint32_t cand, mult;
+    uint64_t tm; /* trace record (parent global id << 12 | candidate, 56 bits) | mult << 56 */
 };
+constexpr int MAX_WORLD = 8;
 
 struct ExpandParams {
     const uint32_t* in;          /* current frontier, n_in states of L::NW words */
     unsigned long long n_in;
     unsigned long long in_base;  /* local id of in[0] */
+    /* frontier spill (BASELINE configs[3]): a frontier buffer may continue in pinned host memory once its part in HBM is full.
+       States [0, in_split) of this launch's view are at `in`, the rest at in_hi (NULL / ~0: no spill); same for out. */
+    const uint32_t* in_hi;
+    unsigned long long in_split;
     uint32_t* out;               /* next frontier */
-    unsigned long long out_cap;
+    uint32_t* out_hi;
+    unsigned long long out_split;
+    unsigned long long out_cap;  /* states the next frontier holds in all (HBM part + host part) */
     unsigned long long out_base; /* local id of out[0] */
     uint64_t* table;             /* capacity entries of {fp, meta} */
-    unsigned long long table_mask;
+    unsigned long long table_cap; /* entries: any multiple of VSR_BUCKET (not only powers of two: memory-bound configs size the seen-set to what is left) */
     uint64_t* trace;             /* per local id: make_trec(parent global id, candidate); may be null */
     unsigned long long trace_cap;
     DevCounters* ctr;
@@ -83,11 +91,17 @@ struct ExpandParams {
     int level;                   /* depth of the states being GENERATED (Init = 1) */
     int check_deadlock;
     int rank, world, owner_shift;/* owner(fp) = fp >> owner_shift (world a power of two; 64 when world = 1) */
-    uint8_t* send;               /* world * send_cap records of (L::BYTES + sizeof(RecHdr)) */
-    unsigned long long send_cap;
-    unsigned int* send_count;    /* world counters */
-    uint64_t* sent_cache;        /* direct-mapped filter of (fingerprint, aux key) pairs already shipped to their owner */
-    unsigned long long sent_mask;
+    /* world > 1.  push[d] = where THIS rank's records for rank d go: its segment of rank d's inbox, in rank d's memory,
+       mapped here over NVLink (CUDA IPC / peer access) — the expand kernel stores them there itself — or a local staging
+       buffer when the host moves them with a collective.  Slots are taken from the local counters send_count[d]. */
+    uint8_t* push[MAX_WORLD];
+    unsigned long long push_cap; /* records per segment */
+    unsigned int* send_count;    /* MAX_WORLD counters, zeroed before every launch */
+    /* records received from rank s in the previous step (the other half of the double-buffered inbox): inserted by this
+       launch after its share of the frontier */
+    const uint8_t* drain[MAX_WORLD];
+    unsigned int drain_n[MAX_WORLD];
+    unsigned long long drain_total;
 };
 
 struct InsertParams {
@@ -110,7 +124,7 @@ __device__ __forceinline__ void cas128(uint64_t* p, uint64_t s0, uint64_t s1, ui
 __device__ __forceinline__ void ld128_cg(const uint64_t* p, uint64_t& a, uint64_t& b) {
     asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
-__device__ __forceinline__ uint64_t mix64(uint64_t x) { /* splitmix64 finaliser: slot index from the fingerprint */
+__device__ __forceinline__ uint64_t mix64(uint64_t x) { /* splitmix64 finaliser */
     x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ULL;
     x ^= x >> 27; x *= 0x94d049bb133111ebULL;
     x ^= x >> 31;
@@ -138,8 +152,10 @@ template <class L, class W> VSR_HD uint32_t check_hash(const W& w, bool use_view
 
 enum { INS_NEW = 0, INS_DUP = 1, INS_TIE = 2, INS_FULL = 3 };
 
-/* global state id = rank << 40 | local id; trace record = global id of the parent << 12 | candidate index
-   (bit 63 is a transient "violates the invariant" mark inside the staging area) */
+/* global state id = rank << 40 | local id (44 bits; all ones = "no parent": Init); trace record = global id of the parent
+   << 12 | candidate index (56 bits; bit 63 is a transient "violates the invariant" mark inside the staging area, bits
+   56..59 carry mult in records that travel between ranks) */
+constexpr unsigned long long GID_MASK = (1ull << 44) - 1ull, ROOT_GID = GID_MASK;
 __host__ __device__ __forceinline__ uint64_t make_gid(int rank, unsigned long long local_id) { return ((uint64_t)rank << 40) | local_id; }
 __host__ __device__ __forceinline__ uint64_t make_trec(uint64_t parent_gid, uint32_t cand) { return (parent_gid << 12) | (cand & 0xFFFu); }
 
@@ -147,25 +163,50 @@ __device__ __forceinline__ uint64_t make_meta(int level, uint32_t auxkey, uint32
     return ((uint64_t)(uint32_t)level << 56) | ((uint64_t)(auxkey & 0xFFFFFFu) << 32) | check;
 }
 
-/* lock-free insert-if-absent; linear probing over 16-byte entries.  (e0, e1) is the entry at the home slot, loaded by the
-   caller as early as the fingerprint was known so that the HBM round trip overlaps the rest of the successor's work. */
-__device__ __forceinline__ unsigned long long table_home(unsigned long long mask, uint64_t fp) {
-#ifdef VSR_EXP_HOME_LOWBITS /* experiment (tools/variants.sh): the Rabin fingerprint's own low bits, no second mix */
-    return fp & mask;
+/* lock-free insert-if-absent over 16-byte entries {fp, meta}.  A probe reads one BUCKET of VSR_BUCKET consecutive entries
+   (1: one 128-bit load; 2: one 256-bit load = a whole 32-byte sector; 4: two 256-bit loads issued together) and walks to
+   the next bucket only when every slot of this one holds another state: the kernel is bound by the LATENCY of dependent
+   probes (profiles/round2_expand_kernel.md), so a wider first probe is paid for in bandwidth the kernel does not use.
+   Slots of a bucket fill in order (no deletions), so a lookup may stop at the first empty slot.  The bucket's entries
+   are loaded by the caller as early as the fingerprint is known so that the HBM round trip overlaps the rest of the
+   successor's work. */
+#ifndef VSR_BUCKET
+#define VSR_BUCKET 1
+#endif
+struct Probe { uint64_t e[2 * VSR_BUCKET]; };
+__device__ __forceinline__ void ld256_cg(const uint64_t* p, uint64_t& a, uint64_t& b, uint64_t& c, uint64_t& d) {
+    asm volatile("ld.global.cg.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p) : "memory");
+}
+__device__ __forceinline__ unsigned long long table_home(unsigned long long cap, uint64_t fp) {
+    /* bucket = floor(hash * nbuckets / 2^64): any capacity, no division.  The hash is the fingerprint times an odd constant
+       (the owner rank is the fingerprint's HIGH bits, so they must not select the bucket on their own) */
+    return __umul64hi(fp * 0x9E3779B97F4A7C15ULL, cap / VSR_BUCKET) * VSR_BUCKET;
+}
+__device__ __forceinline__ void probe_load(const uint64_t* table, unsigned long long h, Probe& p) {
+#if VSR_BUCKET == 1
+    ld128_cg(table + 2 * h, p.e[0], p.e[1]);
+#elif VSR_BUCKET == 2
+    ld256_cg(table + 2 * h, p.e[0], p.e[1], p.e[2], p.e[3]);
+#elif VSR_BUCKET == 4
+    ld256_cg(table + 2 * h, p.e[0], p.e[1], p.e[2], p.e[3]);
+    ld256_cg(table + 2 * h + 4, p.e[4], p.e[5], p.e[6], p.e[7]);
 #else
-    return mix64(fp) & mask;
+#error "VSR_BUCKET must be 1, 2 or 4"
 #endif
 }
-__device__ __forceinline__ int table_insert_from(uint64_t* table, unsigned long long mask, unsigned long long h, uint64_t e0, uint64_t e1,
-                                                 uint64_t fp, uint64_t meta, unsigned& probes, unsigned& collisions) {
+__device__ __forceinline__ int table_insert_from(uint64_t* table, unsigned long long cap, unsigned long long h, Probe p, uint64_t fp, uint64_t meta,
+                                                 unsigned& probes, unsigned& collisions) {
     for (unsigned tries = 0;; tries++) {
         if (tries > (1u << 16)) return INS_FULL; /* the table is (nearly) full: never spin forever, the host aborts with 152 */
         probes++;
-        if (e0 == 0) {
-            cas128(table + 2 * h, fp, meta, e0, e1);
-            if (e0 == 0 && e1 == 0) return INS_NEW;
-        }
-        if (e1 != 0) { /* e1 == 0 with e0 != 0: torn read of an entry being published: look again */
+VSR_UNROLL
+        for (int j = 0; j < VSR_BUCKET; j++) {
+            uint64_t e0 = p.e[2 * j], e1 = p.e[2 * j + 1];
+            if (e0 == 0) {
+                cas128(table + 2 * (h + j), fp, meta, e0, e1);
+                if (e0 == 0 && e1 == 0) return INS_NEW;
+            }
+            for (int again = 0; e1 == 0 && again < 64; again++) ld128_cg(table + 2 * (h + j), e0, e1); /* half-visible entry: look again */
             if (e0 == fp) {
                 if ((uint32_t)e1 == (uint32_t)meta) {
                     const bool same_level = (e1 >> 56) == (meta >> 56);
@@ -174,17 +215,18 @@ __device__ __forceinline__ int table_insert_from(uint64_t* table, unsigned long 
                 }
                 collisions++;
             }
-            h = (h + 1) & mask;
         }
-        ld128_cg(table + 2 * h, e0, e1);
+        h += VSR_BUCKET;
+        if (h >= cap) h = 0;
+        probe_load(table, h, p);
     }
 }
-__device__ __forceinline__ int table_insert(uint64_t* table, unsigned long long mask, uint64_t fp, uint64_t meta,
+__device__ __forceinline__ int table_insert(uint64_t* table, unsigned long long cap, uint64_t fp, uint64_t meta,
                                             unsigned& probes, unsigned& collisions) {
-    const unsigned long long h = table_home(mask, fp);
-    uint64_t e0, e1;
-    ld128_cg(table + 2 * h, e0, e1);
-    return table_insert_from(table, mask, h, e0, e1, fp, meta, probes, collisions);
+    const unsigned long long h = table_home(cap, fp);
+    Probe p;
+    probe_load(table, h, p);
+    return table_insert_from(table, cap, h, p, fp, meta, probes, collisions);
 }
 
 /* TMA bulk store shared -> global of `bytes` (multiple of 16), issued by one lane; waits until the
@@ -197,6 +239,10 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+template <int NW> __device__ __forceinline__ uint32_t* out_state(const ExpandParams& P, unsigned long long i) {
+    return i < P.out_split ? P.out + i * NW : P.out_hi + (i - P.out_split) * NW;
+}
+
 /* ------------------------------------------------------------------ expand kernel */
 
 constexpr int SCAP = 64;      /* staged new states per warp */
@@ -207,11 +253,7 @@ constexpr int QPS = 10;       /* pool entries per parent state (pool = QPS * sta
 #endif
 
 template <class L> struct WarpStage {
-#ifdef VSR_EXP_SKEW
-    alignas(16) uint32_t stage[SCAP * L::NW + 32]; /* + room for the skew of the scratch rows (Expander::scratch) */
-#else
-    alignas(16) uint32_t stage[SCAP * L::NW];    /* new states, packed back to back for the bulk store */
-#endif
+    alignas(16) uint32_t stage[SCAP * L::NW + 32]; /* new states, packed back to back for the bulk store (+ room for the skew of the scratch rows, Expander::scratch) */
     unsigned long long tstage[SCAP];             /* their trace records */
     /* per-warp running state.  It lives here, not in the Expander object: the big per-action routines are real calls
        (one copy of each in the instruction cache), and an object whose address is passed to them would be kept in
@@ -283,7 +325,15 @@ template <class L> struct Expander {
         if (base + n > P.out_cap) {
             if (lane == 0) atomicExch(&P.ctr->overflow, 1);
         } else {
-            if (lane == 0) bulk_store(P.out + base * L::NW, S.stage, (uint32_t)(n * L::BYTES));
+            if (lane == 0) {
+                if (base + n <= P.out_split) bulk_store(P.out + base * L::NW, S.stage, (uint32_t)(n * L::BYTES));
+                else if (base >= P.out_split) bulk_store(P.out_hi + (base - P.out_split) * L::NW, S.stage, (uint32_t)(n * L::BYTES));
+                else { /* the block of ids straddles the end of the HBM part */
+                    const int n1 = (int)(P.out_split - base);
+                    bulk_store(P.out + base * L::NW, S.stage, (uint32_t)(n1 * L::BYTES));
+                    bulk_store(P.out_hi, S.stage + n1 * L::NW, (uint32_t)((n - n1) * L::BYTES));
+                }
+            }
             if (P.trace && lane < n && P.out_base + base + lane < P.trace_cap) P.trace[P.out_base + base + lane] = S.tstage[lane];
         }
         __syncwarp();
@@ -304,119 +354,97 @@ template <class L> struct Expander {
     }
 
     /* fingerprint, route, insert, stage: the part of apply that does not depend on the action */
-#ifdef VSR_EXP_SKEW
-    /* experiment: plain rows, bank conflicts avoided by skewing the row STARTS instead of rotating every access.  Rows of
+    /* this lane's scratch row for the successor it builds: staging rows 32..63 are free whenever a batch starts (fewer than
+       32 states are staged then).  Plain rows, bank conflicts avoided by skewing the row STARTS (measured against rotating
+       every access: 7.5 % less kernel time on the shipped VSR.cfg, profiles/round2_expand_kernel.md).  Rows of
        NW words collide every p = 32 / gcd(NW, 32) lanes; shifting lane l's row by l / p words puts the 32 lanes' word i in
        32 different banks, and an access is base + i: no per-access arithmetic. */
     typedef uint32_t* Row;
     static constexpr int gcd32(int a) { int g = 32; while (a % g) g >>= 1; return g; }
     static constexpr int SKEW_P = 32 / gcd32(L::NW);
     static __device__ __forceinline__ Row scratch(WarpStage<L>& S, int lane) { return &S.stage[(32 + lane) * L::NW + lane / SKEW_P]; }
-#else
-    typedef SwzRow<L::NW> Row;
-    /* this lane's scratch row for the successor it builds: staging rows 32..63 are free whenever a batch starts
-       (fewer than 32 states are staged then), rotated by the lane so equal word indices fall in different banks */
-    static __device__ __forceinline__ Row scratch(WarpStage<L>& S, int lane) { return Row{&S.stage[(32 + lane) * L::NW], lane % L::NW}; }
-#endif
 
-    /* returns this lane's counts for the run's statistics: successors generated (low half) | seen-set probes (high half);
-       the caller keeps the running sums in registers (a warp reduction per batch cost 25 shuffles) */
-#ifdef VSR_EXP_EMIT_UV /* experiment: VIEW on/off decided at the call, one copy of the hash code on the hot path */
-    template <bool UV>
-#endif
-    static __device__ __noinline__ unsigned long long emit(const ExpandParams& P, Smem& B, WarpStage<L>& S, int lane, const Row n, int mult,
-                                                           int cand, int si, bool act) {
+    /* Records for peer ranks (world > 1), pushed by the kernel itself: the lanes of the batch whose successor belongs to
+       another rank lay their records out in destination order in the free half of the warp's staging area (every lane
+       has read its scratch row into registers by now), each destination's run takes its slots in that rank's inbox with
+       ONE atomicAdd on a local counter, and the run leaves as ONE TMA bulk store (cp.async.bulk.global.shared::cta) to
+       the peer's memory — over NVLink when push[] is a peer mapping.  Fire and forget: nothing waits for the remote
+       write, the owner inserts the records in its next launch (drain).  The scratch half holds CAPREC records; a batch
+       with more senders goes in two passes. */
+    static __device__ __forceinline__ void push_records(const ExpandParams& P, WarpStage<L>& S, int lane, const RegRow<L::NW>& v, int send_to, uint64_t fp,
+                                                        uint64_t tm) {
+        const unsigned senders = __ballot_sync(0xffffffffu, send_to >= 0);
+        if (!senders) return;
+        constexpr int RB = L::BYTES + (int)sizeof(RecHdr), RW = RB / 4;
+        constexpr int CAPREC = (32 * L::BYTES) / RB;
+        static_assert(CAPREC >= 16, "two passes must cover a batch");
+        int off = 0, cnt = 0, rnk = 0; /* start of my destination's run in destination order, its length, my place in it */
+        unsigned mymask = 0;
+        for (int d = 0; d < P.world; d++) {
+            const unsigned m = __ballot_sync(0xffffffffu, send_to == d);
+            if (send_to > d) off += __popc(m);
+            if (send_to == d) { mymask = m; cnt = __popc(m); rnk = __popc(m & ((1u << lane) - 1u)); }
+        }
+        unsigned base = 0;
+        if (send_to >= 0 && rnk == 0) base = atomicAdd(&P.send_count[send_to], (unsigned)cnt);
+        base = __shfl_sync(0xffffffffu, base, mymask ? __ffs(mymask) - 1 : 0);
+        const bool fits = send_to >= 0 && (unsigned long long)base + (unsigned)cnt <= P.push_cap;
+        if (send_to >= 0 && !fits && rnk == 0) atomicExch(&P.ctr->overflow, 3);
+        const int pos = off + rnk, total = __popc(senders);
+        uint32_t* sbuf = &S.stage[32 * L::NW];
+        for (int lo = 0; lo < total; lo += CAPREC) {
+            const int hi = lo + CAPREC < total ? lo + CAPREC : total;
+            if (send_to >= 0 && pos >= lo && pos < hi) {
+                uint32_t* r = sbuf + (pos - lo) * RW;
+                VSR_UNROLL
+                for (int j = 0; j < L::NW; j++) r[j] = v.w[j];
+                r[L::NW] = (uint32_t)fp; r[L::NW + 1] = (uint32_t)(fp >> 32);
+                r[L::NW + 2] = (uint32_t)tm; r[L::NW + 3] = (uint32_t)(tm >> 32);
+            }
+            __syncwarp();
+            if (fits) {
+                const int st = off > lo ? off : lo, en = off + cnt < hi ? off + cnt : hi;
+                if (pos == st && st < en)
+                    bulk_store(P.push[send_to] + (size_t)(base + (unsigned)(st - off)) * RB, sbuf + (st - lo) * RW, (uint32_t)((en - st) * RB));
+            }
+            __syncwarp();
+        }
+    }
+
+    /* the seen-set insert of one state per lane and everything after it — tie list, inline invariant, compaction of the
+       survivors into the warp's staging area, flush — shared by the expansion (emit) and by the records received from
+       peers (drain).  Returns this lane's counts for the run's statistics: successors generated (low half) | seen-set
+       probes (high half); the caller keeps the running sums in registers (a warp reduction per batch cost 25 shuffles) */
+    static __device__ __forceinline__ unsigned long long commit(const ExpandParams& P, WarpStage<L>& S, int lane, const RegRow<L::NW>& v, bool live, uint64_t fp,
+                                                                uint32_t chk, uint32_t auxkey, unsigned long long home, const Probe& first, unsigned long long trec,
+                                                                unsigned mult) {
         unsigned gen = 0, probes = 0, coll = 0;
         int sn = S.sn;
-        int send_to = -1;
-        uint64_t s_fp = 0, s_meta = 0, s_parent = 0;
         bool isnew = false;
         int bad = 0;
-        unsigned long long trec = 0;
-        /* the successor's words, read once from the lane's scratch row: fingerprint, check hash, aux key, invariant and
-           the copies to the staging area / a peer's send buffer all work on registers (constant word indices) */
-        RegRow<L::NW> v;
-        if (act && mult > 0) {
-            VSR_UNROLL
-            for (int j = 0; j < L::NW; j++) v.w[j] = rdw(n, j);
-        }
-        if (act) {
-            if (mult < 0) {
-                atomicCAS(&P.ctr->error, 0, mult);
-            } else if (mult > 0) {
-#ifdef VSR_EXP_EMIT_UV
-                uint64_t fp = fp64_view8_t<L, UV>(B.fp_tab, v);
-#else
-                uint64_t fp = fp64_view8<L>(B.fp_tab, v, P.run.use_view != 0);
-#endif
-                if (fp == 0) fp = 1;
-                const int owner = P.world > 1 ? (int)(fp >> P.owner_shift) : P.rank;
-                /* start the seen-set probe now; the check hash, aux key and tags are computed under its latency */
-                const unsigned long long home = table_home(P.table_mask, fp);
-                ulonglong2 first = make_ulonglong2(0, 0);
-                if (owner == P.rank) first = __ldcg(reinterpret_cast<const ulonglong2*>(P.table + 2 * home));
-#ifdef VSR_EXP_EMIT_UV
-                const uint32_t chk = check_hash_t<L, UV>(v);
-#else
-                const uint32_t chk = check_hash<L>(v, P.run.use_view != 0);
-#endif
-                const uint32_t auxkey = O_::aux_key(v);
-                const uint64_t meta = make_meta(P.level, auxkey, chk);
-                const uint64_t parent_gid = make_gid(P.rank, P.in_base + B.round_first + si);
-                trec = make_trec(parent_gid, (uint32_t)cand);
-                if (owner == P.rank) {
-                    gen += (unsigned)mult; /* successors sent to a peer are counted where they are inserted */
-                    const int r = table_insert_from(P.table, P.table_mask, home, first.x, first.y, fp, meta, probes, coll);
-                    isnew = r == INS_NEW;
-                    if (r == INS_FULL) atomicExch(&P.ctr->overflow, 4);
-                    if (isnew) bad = O_::invariant(P.run, v);
-                    if (coll) atomicAdd(&P.ctr->collisions, (unsigned long long)coll); /* never seen so far */
-                    if (r == INS_TIE) {
-                        atomicAdd(&P.ctr->ties, 1ull);
-                        const unsigned long long t = atomicAdd(&P.ctr->tie_count, 1ull);
-                        if (t < P.tie_cap) {
-                            TieRec rec;
-                            rec.fp = fp; rec.parent = parent_gid; rec.auxkey = auxkey; rec.cand = (uint32_t)cand; rec.check = chk; rec._pad = 0;
-                            uint8_t* dst = P.ties + t * (sizeof(TieRec) + L::BYTES);
-                            *(TieRec*)dst = rec;
-                            VSR_UNROLL
-                            for (int j = 0; j < L::NW; j++) ((uint32_t*)(dst + sizeof(TieRec)))[j] = v.w[j];
-                        } else atomicExch(&P.ctr->overflow, 2);
-                    }
-                } else if (P.sent_cache && P.sent_cache[mix64(fp ^ auxkey) & P.sent_mask] == (fp ^ ((uint64_t)auxkey << 40))) {
-                    /* this exact (VIEW, aux) pair was already shipped to its owner earlier in the run: a duplicate for
-                       sure, so it is counted here and not sent again (most generated successors are duplicates) */
-                    gen += (unsigned)mult;
-                } else {
-                    if (P.sent_cache) P.sent_cache[mix64(fp ^ auxkey) & P.sent_mask] = fp ^ ((uint64_t)auxkey << 40);
-                    send_to = owner;
-                    s_fp = fp; s_meta = meta; s_parent = parent_gid;
-                }
-            }
-        }
-        /* records for peers: the lanes of this batch that send to the same rank take their slots with ONE atomicAdd
-           (a per-record atomic on `world` hot counters serialises the whole GPU) */
-        if (P.world > 1) {
-            const unsigned senders = __ballot_sync(0xffffffffu, send_to >= 0);
-            if (send_to >= 0) {
-                const unsigned peers = __match_any_sync(senders, send_to);
-                const int leader = __ffs(peers) - 1;
-                unsigned base = 0;
-                if (lane == leader) base = atomicAdd(&P.send_count[send_to], (unsigned)__popc(peers));
-                base = __shfl_sync(peers, base, leader);
-                const unsigned idx = base + __popc(peers & ((1u << lane) - 1u));
-                if (idx < P.send_cap) {
-                    uint8_t* rec = P.send + ((size_t)send_to * P.send_cap + idx) * (L::BYTES + sizeof(RecHdr));
-                    uint32_t* rw = (uint32_t*)rec;
+        if (live) {
+            const uint64_t meta = make_meta(P.level, auxkey, chk);
+            gen = mult;
+            const int r = table_insert_from(P.table, P.table_cap, home, first, fp, meta, probes, coll);
+            isnew = r == INS_NEW;
+            if (r == INS_FULL) atomicExch(&P.ctr->overflow, 4);
+            if (isnew) bad = O_::invariant(P.run, v);
+            if (coll) atomicAdd(&P.ctr->collisions, (unsigned long long)coll); /* never seen so far */
+            if (r == INS_TIE) {
+                atomicAdd(&P.ctr->ties, 1ull);
+                const unsigned long long t = atomicAdd(&P.ctr->tie_count, 1ull);
+                if (t < P.tie_cap) {
+                    TieRec rec;
+                    rec.fp = fp; rec.parent = trec >> 12; rec.auxkey = auxkey; rec.cand = (uint32_t)(trec & 0xFFFu); rec.check = chk; rec._pad = 0;
+                    uint8_t* dst = P.ties + t * (sizeof(TieRec) + L::BYTES);
+                    *(TieRec*)dst = rec;
                     VSR_UNROLL
-                    for (int j = 0; j < L::NW; j++) rw[j] = v.w[j];
-                    RecHdr* h = (RecHdr*)(rec + L::BYTES);
-                    h->fp = s_fp; h->meta = s_meta; h->parent = s_parent; h->cand = (uint32_t)cand; h->mult = (uint32_t)mult;
-                } else atomicExch(&P.ctr->overflow, 3);
+                    for (int j = 0; j < L::NW; j++) ((uint32_t*)(dst + sizeof(TieRec)))[j] = v.w[j];
+                } else atomicExch(&P.ctr->overflow, 2);
             }
         }
         /* compaction of the survivors into the warp's staging area (one ballot, all lanes).  The survivors' final rows
-           may overlap other lanes' scratch rows: every lane has read its row (above) before anybody writes */
+           may overlap other lanes' scratch rows: every lane has read its row before anybody writes */
         const unsigned newmask = __ballot_sync(0xffffffffu, isnew);
         __syncwarp();
         if (isnew) {
@@ -438,6 +466,92 @@ template <class L> struct Expander {
             sn -= 32;
         }
         return (unsigned long long)gen | ((unsigned long long)probes << 32);
+    }
+
+    /* fingerprint and route one successor per lane: the part of apply that does not depend on the action */
+    static __device__ __noinline__ unsigned long long emit(const ExpandParams& P, Smem& B, WarpStage<L>& S, int lane, const Row n, int mult,
+                                                           int cand, int si, bool act) {
+        int send_to = -1;
+        uint64_t fp = 0;
+        uint32_t chk = 0, auxkey = 0;
+        unsigned long long home = 0, trec = 0;
+        Probe first = {};
+        bool live = false;
+        /* the successor's words, read once from the lane's scratch row: fingerprint, check hash, aux key, invariant and
+           the copies to the staging area / a peer's inbox all work on registers (constant word indices) */
+        RegRow<L::NW> v;
+        if (act && mult > 0) {
+            VSR_UNROLL
+            for (int j = 0; j < L::NW; j++) v.w[j] = rdw(n, j);
+        }
+        if (act) {
+            if (mult < 0) {
+                atomicCAS(&P.ctr->error, 0, mult);
+            } else if (mult > 0) {
+                fp = fp64_view8<L>(B.fp_tab, v, P.run.use_view != 0);
+                if (fp == 0) fp = 1;
+                const int owner = P.world > 1 ? (int)(fp >> P.owner_shift) : P.rank;
+                trec = make_trec(make_gid(P.rank, P.in_base + B.round_first + si), (uint32_t)cand);
+                if (owner == P.rank) {
+                    /* start the seen-set probe now; the check hash, aux key and tags are computed under its latency */
+                    live = true;
+                    home = table_home(P.table_cap, fp);
+                    probe_load(P.table, home, first);
+                    chk = check_hash<L>(v, P.run.use_view != 0);
+                    auxkey = O_::aux_key(v);
+                } else {
+                    send_to = owner; /* counted ("states generated") where it is inserted */
+                }
+            }
+        }
+        if (P.world > 1) {
+            __syncwarp(); /* every lane has read its scratch row: that half of the staging area may now carry outgoing records */
+            push_records(P, S, lane, v, send_to, fp, trec | ((uint64_t)(unsigned)mult << 56));
+        }
+        return commit(P, S, lane, v, live, fp, chk, auxkey, home, first, trec, (unsigned)mult);
+    }
+
+    /* ---- drain: one record received from a peer per lane (world > 1).  The sender computed the fingerprint; check hash
+       and aux key are recomputed from the words; then the same seen-set insert / invariant / staging as a local successor */
+    __device__ __forceinline__ void drain_chunk(unsigned long long firstrec) {
+        constexpr int RB = L::BYTES + (int)sizeof(RecHdr);
+        unsigned long long i = firstrec + lane;
+        const bool have = i < P.drain_total;
+        RegRow<L::NW> v;
+        uint64_t fp = 0, tm = 0;
+        uint32_t chk = 0, auxkey = 0;
+        unsigned long long home = 0;
+        Probe first = {};
+        if (have) {
+            int s = 0;
+            while (s < P.world - 1 && i >= P.drain_n[s]) { i -= P.drain_n[s]; s++; }
+            const uint4* r = reinterpret_cast<const uint4*>(P.drain[s] + i * RB);
+            const uint4 h = __ldcs(r + L::NW / 4);
+            fp = ((uint64_t)h.y << 32) | h.x;
+            tm = ((uint64_t)h.w << 32) | h.z;
+            home = table_home(P.table_cap, fp);
+            probe_load(P.table, home, first);
+            VSR_UNROLL
+            for (int q = 0; q < L::NW / 4; q++) {
+                const uint4 x = __ldcs(r + q);
+                v.w[4 * q] = x.x; v.w[4 * q + 1] = x.y; v.w[4 * q + 2] = x.z; v.w[4 * q + 3] = x.w;
+            }
+            chk = check_hash<L>(v, P.run.use_view != 0);
+            auxkey = O_::aux_key(v);
+        }
+        tally(commit(P, S, lane, v, have, fp, chk, auxkey, home, first, tm & ((1ull << 56) - 1ull), (unsigned)((tm >> 56) & 0xFu)));
+    }
+    __device__ void drain() {
+        const unsigned long long nchunks = (P.drain_total + 31) / 32;
+        unsigned long long c = 0;
+        if (lane == 0) c = atomicAdd(&P.ctr->drain_next, 1ull);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        while (c < nchunks) {
+            unsigned long long nx = 0;
+            if (lane == 0) nx = atomicAdd(&P.ctr->drain_next, 1ull); /* the next claim's latency hides under this chunk */
+            drain_chunk(c * 32);
+            c = __shfl_sync(0xffffffffu, nx, 0);
+        }
     }
 
     /* ---- scan: guards only, from registers.  Each thread copies its own state into registers and evaluates every guard
@@ -552,11 +666,7 @@ template <class L> struct Expander {
         const Row n = scratch(S, lane);
         int mult = 0;
         if (act) mult = O_::template step_grp<true, G>(P.run, parent, cand, n);
-#ifdef VSR_EXP_EMIT_UV
-        return P.run.use_view ? emit<true>(P, B, S, lane, n, mult, cand, si, act) : emit<false>(P, B, S, lane, n, mult, cand, si, act);
-#else
         return emit(P, B, S, lane, n, mult, cand, si, act);
-#endif
     }
     /* one batch of <= 32 queued pairs of group G, pool[b .. b + k) */
     template <int G> static __device__ __forceinline__ unsigned long long batch(const ExpandParams& P, Smem& B, WarpStage<L>& S, int lane, int b,
@@ -579,19 +689,15 @@ template <class L> struct Expander {
     __device__ void run_round(unsigned long long first, int count) {
         /* coalesced load of `count` parent states into padded rows */
         const uint32_t* src = P.in + first * L::NW;
-#ifdef VSR_EXP_PAR128 /* experiment: 16-byte loads (states are whole 16-byte units), a quarter of the index arithmetic */
-        {
-            constexpr int Q = L::NW / 4;
-            const uint4* src4 = reinterpret_cast<const uint4*>(src);
-            for (int i = tid; i < count * Q; i += NS) {
-                const uint4 v = __ldg(src4 + i);
-                uint32_t* d = &B.par[(i / Q) * (L::NW + 1) + (i % Q) * 4];
-                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        if (first + count <= P.in_split) {
+            for (int i = tid; i < count * L::NW; i += NS) B.par[(i / L::NW) * (L::NW + 1) + (i % L::NW)] = __ldg(src + i);
+        } else { /* (part of) this round's parents are in the host part of the frontier */
+            for (int i = tid; i < count * L::NW; i += NS) {
+                const unsigned long long st = first + i / L::NW;
+                const uint32_t* row = st < P.in_split ? P.in + st * L::NW : P.in_hi + (st - P.in_split) * L::NW;
+                B.par[(i / L::NW) * (L::NW + 1) + (i % L::NW)] = __ldg(row + i % L::NW);
             }
         }
-#else
-        for (int i = tid; i < count * L::NW; i += NS) B.par[(i / L::NW) * (L::NW + 1) + (i % L::NW)] = __ldg(src + i);
-#endif
         if (tid < Smem::NG) B.qcount[tid] = 0;
         if (tid == 0) { B.round_first = first; B.take = 0; }
         __syncthreads();
@@ -674,19 +780,19 @@ template <class L> __global__ void __launch_bounds__(ExpandCfg<L>::WARPS * 32, 2
         /* claim the round after this one now: the global atomic's latency hides under this round's work */
         if (threadIdx.x == 0) {
             next_round = atomicAdd(&P.ctr->work_next, 1ull);
-#ifdef VSR_EXP_PREFETCH /* experiment: pull the next round's parents into L2 while this round runs */
+            /* pull the next round's parents into L2 while this round runs */
             const unsigned long long nx = next_round;
-            if (nx < nrounds) {
+            if (nx < nrounds && (nx + 1) * Smem::NS <= P.in_split) {
                 const unsigned long long nfirst = nx * Smem::NS;
                 const unsigned long long ncount = (P.n_in - nfirst) < (unsigned long long)Smem::NS ? (P.n_in - nfirst) : Smem::NS;
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.in + nfirst * L::NW), "r"((uint32_t)(ncount * L::BYTES)) : "memory");
             }
-#endif
         }
         const unsigned long long first = c * Smem::NS;
         const int count = (int)((P.n_in - first) < (unsigned long long)Smem::NS ? (P.n_in - first) : Smem::NS);
         X.run_round(first, count);
     }
+    if (P.drain_total) X.drain();
     X.finish();
 }
 
@@ -703,19 +809,23 @@ template <class L> __global__ void __launch_bounds__(256) insert_kernel(const In
     const RecHdr* h = (const RecHdr*)(rec + L::BYTES);
     unsigned probes = 0, coll = 0, nties = 0;
     unsigned long long gen = 0;
+    uint64_t parent = 0;
+    uint32_t cand = 0;
     if (have) {
-        /* meta == 0: the sender (host seeding Init) left tag computation to the device */
-        const uint64_t meta = h->meta ? h->meta : make_meta(P.level, Ops<L>::aux_key(n), check_hash<L>(n, P.run.use_view != 0));
-        const int r = table_insert(P.table, P.table_mask, h->fp, meta, probes, coll);
+        /* check hash and aux key are computed here from the words; the header carries the fingerprint, the trace record and mult */
+        const uint64_t meta = make_meta(P.level, Ops<L>::aux_key(n), check_hash<L>(n, P.run.use_view != 0));
+        const int r = table_insert(P.table, P.table_cap, h->fp, meta, probes, coll);
         isnew = r == INS_NEW;
         if (r == INS_FULL) atomicExch(&P.ctr->overflow, 4);
-        gen = h->mult;
+        gen = (h->tm >> 56) & 0xFu;
+        parent = (h->tm >> 12) & ((1ull << 44) - 1ull);
+        cand = (uint32_t)(h->tm & 0xFFFu);
         if (r == INS_TIE) {
             nties = 1;
             const unsigned long long t = atomicAdd(&P.ctr->tie_count, 1ull);
             if (t < P.tie_cap) {
                 TieRec tr;
-                tr.fp = h->fp; tr.parent = h->parent; tr.auxkey = (uint32_t)((meta >> 32) & 0xFFFFFF); tr.cand = h->cand;
+                tr.fp = h->fp; tr.parent = parent; tr.auxkey = (uint32_t)((meta >> 32) & 0xFFFFFF); tr.cand = cand;
                 tr.check = (uint32_t)meta; tr._pad = 0;
                 uint8_t* dst = P.ties + t * (sizeof(TieRec) + L::BYTES);
                 *(TieRec*)dst = tr;
@@ -745,9 +855,9 @@ template <class L> __global__ void __launch_bounds__(256) insert_kernel(const In
         if (isnew) {
             const unsigned long long pos = base + __popc(newmask & ((1u << lane) - 1u));
             if (pos < P.out_cap) {
-                uint32_t* dst = P.out + pos * L::NW;
+                uint32_t* dst = out_state<L::NW>(P, pos);
                 for (int j = 0; j < L::NW; j++) dst[j] = n[j];
-                if (P.trace && P.out_base + pos < P.trace_cap) P.trace[P.out_base + pos] = make_trec(h->parent, h->cand);
+                if (P.trace && P.out_base + pos < P.trace_cap) P.trace[P.out_base + pos] = make_trec(parent, cand);
                 const int bad = Ops<L>::invariant(P.run, n);
                 if (bad) {
                     atomicMin(&P.ctr->viol_id, P.out_base + pos);
@@ -767,7 +877,7 @@ template <class L> __global__ void patch_ties_kernel(const ExpandParams P, const
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_out) return;
     uint32_t w[L::NW];
-    uint32_t* st = P.out + i * L::NW;
+    uint32_t* st = out_state<L::NW>(P, i);
     for (int j = 0; j < L::NW; j++) w[j] = st[j];
     uint64_t fp = fp64_view8<L>(P.fp_tab, w, P.run.use_view != 0);
     if (fp == 0) fp = 1;
@@ -796,13 +906,13 @@ template <class L> __global__ void patch_ties_kernel(const ExpandParams P, const
 }
 
 /* membership query (tests / golden-trace cross-check): meta of the entry holding (fp, check), 0 if absent */
-__global__ void lookup_kernel(const uint64_t* table, unsigned long long mask, uint64_t fp, uint32_t check, unsigned long long* meta_out) {
-    unsigned long long h = mix64(fp) & mask;
-    for (unsigned long long i = 0; i <= mask; i++) {
+static __global__ void lookup_kernel(const uint64_t* table, unsigned long long cap, uint64_t fp, uint32_t check, unsigned long long* meta_out) {
+    unsigned long long h = table_home(cap, fp);
+    for (unsigned long long i = 0; i < cap; i++) {
         const uint64_t e0 = table[2 * h], e1 = table[2 * h + 1];
         if (e0 == 0) { *meta_out = 0; return; }
         if (e0 == fp && (uint32_t)e1 == check) { *meta_out = e1; return; }
-        h = (h + 1) & mask;
+        if (++h >= cap) h = 0;
     }
     *meta_out = 0;
 }
@@ -857,7 +967,7 @@ template <class L> __global__ void simulate_kernel(const SimParams Q) {
 
 /* seen-set micro-benchmark: n splitmix64 keys, a fraction of them duplicates, inserted with the same
    table_insert the BFS uses; nothing else in the loop, so its rate is the random-probe ceiling of this table design */
-__global__ void probe_bench_kernel(uint64_t* table, unsigned long long mask, unsigned long long n, unsigned long long distinct,
+static __global__ void probe_bench_kernel(uint64_t* table, unsigned long long cap, unsigned long long n, unsigned long long distinct,
                                    unsigned long long seed, unsigned long long* new_count, unsigned long long* probe_count) {
     unsigned long long mine_new = 0;
     unsigned probes = 0, coll = 0;
@@ -867,7 +977,7 @@ __global__ void probe_bench_kernel(uint64_t* table, unsigned long long mask, uns
         z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
         z ^= z >> 31;
         if (z == 0) z = 1;
-        mine_new += table_insert(table, mask, z, make_meta(1, 0, (uint32_t)(z >> 32) | 1u), probes, coll) == INS_NEW;
+        mine_new += table_insert(table, cap, z, make_meta(1, 0, (uint32_t)(z >> 32) | 1u), probes, coll) == INS_NEW;
     }
     for (int o = 16; o; o >>= 1) {
         mine_new += __shfl_xor_sync(0xffffffffu, mine_new, o);

@@ -165,6 +165,32 @@ static void set_err(char* err, size_t cap, const std::string& msg) {
 
 /* ------------------------------------------------------------------ .tla identity check */
 
+/* FNV-1a 64 of the spec text without comments ("\\*" to end of line, "(* ... *)" nested), without trailing blanks, without
+   empty lines and with LF line ends; leading indentation is kept (junction lists are layout-sensitive in TLA+). */
+uint64_t vsr_normalised_spec_hash(const std::string& text) {
+    std::string out, line;
+    int depth = 0;
+    auto flush = [&]() {
+        size_t e = line.find_last_not_of(" \t\r");
+        if (e != std::string::npos) { out.append(line, 0, e + 1); out.push_back('\n'); }
+        line.clear();
+    };
+    for (size_t i = 0; i < text.size(); i++) {
+        const char c = text[i], d = i + 1 < text.size() ? text[i + 1] : 0;
+        if (depth == 0 && c == '\\' && d == '*') { while (i < text.size() && text[i] != '\n') i++; flush(); continue; }
+        if (c == '(' && d == '*') { depth++; i++; continue; }
+        if (depth > 0 && c == '*' && d == ')') { depth--; i++; continue; }
+        if (c == '\n') { flush(); continue; }
+        if (depth == 0) line.push_back(c);
+    }
+    flush();
+    uint64_t h = 0xcbf29ce484222325ULL;
+    for (unsigned char c : out) { h ^= c; h *= 0x100000001b3ULL; }
+    return h;
+}
+/* vsr-revisited/paper/VSR.tla @ 7566e8af (the revision SURVEY.md and every file:line citation in this repo refer to) */
+static const uint64_t VSR_TLA_NORMALISED_HASH = 0x2b832f2080e8649cULL;
+
 static int verify_tla(const char* path, VsrModel* m, std::string& why) {
     std::ifstream f(path, std::ios::binary);
     if (!f) { why = std::string("cannot read spec ") + path; return VSR_RC_SPEC_ERROR; }
@@ -174,6 +200,24 @@ static int verify_tla(const char* path, VsrModel* m, std::string& why) {
     uint64_t h = 0xcbf29ce484222325ULL;
     for (unsigned char c : text) { h ^= c; h *= 0x100000001b3ULL; }
     m->info.spec_hash = h;
+    /* The actions and invariants are hand-lowered, so the FILE must be the spec that was lowered: checking the structure
+       below is not enough (an edited guard or invariant body would pass it and be "verified" against the built-in
+       lowering).  Compare a hash of the text normalised for line ends, trailing blanks, blank lines and comments. */
+    const uint64_t nh = vsr_normalised_spec_hash(text);
+    const bool pinned = nh == VSR_TLA_NORMALISED_HASH;
+    if (!pinned) {
+        const char* allow = getenv("VSR_B200_ALLOW_EDITED_SPEC");
+        if (!(allow && allow[0] == '1')) {
+            char buf[320];
+            snprintf(buf, sizeof buf, "%s is not the VSR.tla this checker lowers by hand (normalised text hash %016llx, expected %016llx): Next and the "
+                     "invariants are compiled in, so an edited spec would be checked against the ORIGINAL definitions", path, (unsigned long long)nh,
+                     (unsigned long long)VSR_TLA_NORMALISED_HASH);
+            why = buf;
+            return VSR_RC_SPEC_ERROR;
+        }
+        fprintf(stderr, "WARNING: %s differs from the VSR.tla this checker lowers (VSR_B200_ALLOW_EDITED_SPEC=1): the BUILT-IN Next and invariants are "
+                        "checked, NOT the definitions in this file; the spec is reported as unverified\n", path);
+    }
     std::vector<std::string> lines;
     {
         std::string cur;
@@ -265,7 +309,7 @@ static int verify_tla(const char* path, VsrModel* m, std::string& why) {
             break;
         }
     }
-    m->info.spec_verified = 1;
+    m->info.spec_verified = pinned ? 1 : 0;
     return 0;
 }
 
@@ -767,6 +811,7 @@ void vsr_model_free(VsrModel* m) { delete m; }
 int vsr_model_info(const VsrModel* m, VsrModelInfo* out) {
     if (!m || !out) return VSR_RC_ERROR;
     *out = m->info;
+    out->check_deadlock = m->check_deadlock_cfg;
     return 0;
 }
 

@@ -42,7 +42,7 @@ struct ModelOps {
     int (*enabled_list)(const RunCfg*, const uint32_t*, uint32_t* out); /* register-mask form of the guards (the kernel's scan) */
 };
 /* bump when ModelOps / GpuOps / ExpandParams change shape: a layout plug-in built against another value is rebuilt */
-#define VSR_PLUGIN_ABI 3
+#define VSR_PLUGIN_ABI 4
 const ModelOps* find_model_ops(int R, int V, int K);
 const GpuOps* find_gpu_ops(int R, int V, int K); /* defined in vsr_gpu.cu */
 
