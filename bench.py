@@ -29,12 +29,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(R=3, V=2, L=2)           # BASELINE configs[1] = vsr-revisited/paper/VSR.cfg
-TABLE_CAP = 1 << int(os.environ.get("VSR_BENCH_TABLE_LOG2", "31"))  # 2^31 slots * 16 B = 32 GiB (1.17e9 states -> load 0.55) + 15 GiB of trace records
+TABLE_CAP = 1 << int(os.environ.get("VSR_BENCH_TABLE_LOG2", "32"))  # 2^32 slots * 16 B = 64 GiB over all GPUs (1.17e9 states -> load 0.27: measured 10 %
+                                                                     # less kernel time than 2^31, profiles/round2_expand_kernel.md) + 8 B of trace record per slot
 FRONTIER_CAP = 140_000_000               # widest level: 120,193,500 states
 EXPECT = dict(distinct=1173992337, generated=3129587684, depth=47, violation_level=28)
-# a configuration BOTH arms finish: (R=3, V=2, L=1) complete = 697,364 distinct states, depth 30 (pinned to the spec's text,
-# tests/golden/spec_text_results.json) - the same-config comparison beside the bounded cfg2 sample of the CPU arm
-SMALL = dict(R=3, V=2, L=1, distinct=697364, generated=1831657, depth=30)
+# a configuration BOTH arms finish: (R=3, V=2, L=1) WITHOUT SYMMETRY, complete = 697,364 distinct states, depth 30 - totals pinned to
+# the spec's text (tests/golden/spec_text_results.json) - the same-config comparison beside the bounded cfg2 sample of the CPU arm
+SMALL = dict(R=3, V=2, L=1, symmetry=0, distinct=697364, generated=1831657, depth=30)
 # BASELINE configs[2]/[4]: README constants to the first AcknowledgedWriteNotLost violation (needs >= 4 GPUs of memory)
 CFG3 = dict(R=3, V=3, L=3, violation_level=24, distinct=3166753191, table_total=1 << 33, frontier_total=1_600_000_000)
 
@@ -125,7 +126,7 @@ def oracle_sample(seconds, workers, cfg=None):
     lib.orc_bfs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_double, C.c_int, C.c_int, C.c_int, C.c_char_p,
                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
     cfg = cfg or WORKLOAD
-    q = (C.c_int * 8)(cfg["R"], 1, cfg["V"], cfg["L"], 0, 1, 1, 0)  # invariant 0: explore, do not stop
+    q = (C.c_int * 8)(cfg["R"], 1, cfg["V"], cfg["L"], 0, cfg.get("symmetry", 1), 1, 0)  # invariant 0: explore, do not stop
     scal = (C.c_uint64 * 32)()
     lv = (C.c_uint64 * 512)()
     t0 = time.time()
@@ -138,7 +139,7 @@ def small_complete_cpu(cores):
     """the same-config leg of the CPU arm: (R=3, V=2, L=1) to completion on all cores"""
     s = oracle_sample(0.0, cores, SMALL)
     ok = (s["distinct"], s["generated"], s["depth"]) == (SMALL["distinct"], SMALL["generated"], SMALL["depth"])
-    return {"workload": "VSR.tla ReplicaCount=3 Values={v1,v2} StartViewOnTimerLimit=1, COMPLETE state space (%d distinct states, depth %d)"
+    return {"workload": "VSR.tla ReplicaCount=3 Values={v1,v2} StartViewOnTimerLimit=1 VIEW view, no SYMMETRY: COMPLETE state space (%d distinct states, depth %d)"
                         % (SMALL["distinct"], SMALL["depth"]),
             "value": s["rate"], "unit": "states/s", "seconds": s["seconds"], "cores": cores, "kind": "port", "results_match_expected": ok}
 
@@ -276,6 +277,9 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cfg3", action="store_true", help="N >= 4: skip the README-constants first-violation block")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the end-to-end legs")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "staged"],
+                    help="N > 1: p2p = the kernel stores remote successors into the owner's inbox over NVLink, C++ level loop (default); "
+                         "staged = the baseline it replaces: local staging buffer + NCCL send/recv per step, Python level loop")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -304,7 +308,10 @@ def main():
     S = mc.state_bytes
     table_cap = TABLE_CAP // world
     frontier_cap = FRONTIER_CAP // world + 4_000_000
-    eng = vdist.GpuEngine(mc, rank, world, device=local, table_capacity=table_cap, frontier_capacity=frontier_cap, keep_trace=True, group=group)
+    staged = world > 1 and args.exchange == "staged"
+    eng = vdist.GpuEngine(mc, rank, world, device=local, table_capacity=table_cap, frontier_capacity=frontier_cap, keep_trace=True, group=group,
+                          exchange=args.exchange)
+    pump = vdist.ShardedBfs(eng, rank, world) if staged else None
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -313,6 +320,10 @@ def main():
         torch.cuda.synchronize(dev)
 
     def one_step():
+        if staged:
+            r = pump.run(stop_on_violation=False, want_trace=False)
+            r.launches = int(eng.stats().kernel_launches)
+            return r
         return eng.run(stop_on_violation=False, want_trace=False)
 
     for _ in range(args.warmup):
@@ -386,7 +397,7 @@ def main():
     # -> BFS -> stats and counterexample back in host memory -> teardown.  Allocating and clearing tens of GB varies with the
     # box's allocator state, so three runs, median reported, all three in the JSON.
     e2e_runs, e2e_states, h2d, d2h = [], 0, 0, 0
-    for _ in range(0 if args.no_e2e else 3):
+    for _ in range(0 if (args.no_e2e or staged) else 3):
         barrier()
         te = time.time()
         if world == 1:
@@ -395,13 +406,9 @@ def main():
             ok = ok and r2.distinct == EXPECT["distinct"] and r2.rc == 12 and len(r2.trace) == EXPECT["violation_level"]
         else:
             mc2 = pkg.ModelChecker.from_cfg_text(cfg)
-            eng2 = vdist.GpuEngine(mc2, rank, world, device=local, table_capacity=table_cap, frontier_capacity=frontier_cap, keep_trace=True, group=group)
-            r2 = eng2.run(stop_on_violation=False, want_trace=True)
-            tr = vdist.replay_trace(mc2, r2.trace_cands) if rank == 0 else []
-            st2 = eng2.stats()
-            e2e_states, h2d, d2h = r2.distinct, int(st2.bytes_h2d) + len(cfg), int(st2.bytes_d2h) + C.sizeof(pkg.checker.VsrStats)
-            ok = ok and r2.distinct == EXPECT["distinct"] and r2.rc == 12 and (rank != 0 or len(tr) == EXPECT["violation_level"])
-            eng2.close()
+            r2 = vdist.check_sharded(mc2, group, device=local, table_capacity=table_cap, frontier_capacity=frontier_cap, stop_on_violation=False)
+            e2e_states, h2d, d2h = r2.distinct, r2.bytes_h2d + len(cfg), r2.bytes_d2h + C.sizeof(pkg.checker.VsrStats)
+            ok = ok and r2.distinct == EXPECT["distinct"] and r2.rc == 12 and (rank != 0 or len(r2.trace) == EXPECT["violation_level"])
         barrier()
         t = torch.tensor([time.time() - te], dtype=torch.float64, device=dev)
         if world > 1:
@@ -410,7 +417,7 @@ def main():
     e2e_s = sorted(e2e_runs)[1] if e2e_runs else None
 
     cfg3 = None
-    if world >= 4 and not args.no_cfg3:
+    if world >= 4 and not args.no_cfg3 and not staged:
         try:
             cfg3 = cfg3_first_violation(pkg, vdist, torch, tdist, group, rank, world, local, dev, barrier)
         except pkg.VsrError as ex:
@@ -418,7 +425,7 @@ def main():
 
     small_gpu = None
     if world == 1 and rank == 0:
-        mcs = pkg.ModelChecker.from_constants(SMALL["R"], SMALL["V"], SMALL["L"])
+        mcs = pkg.ModelChecker.from_constants(SMALL["R"], SMALL["V"], SMALL["L"], symmetry=False)
         ts = time.time()
         rs = mcs.check(stop_on_violation=False, table_capacity=1 << 22, frontier_capacity=1 << 19)
         small_gpu = {"value": rs.distinct / (time.time() - ts), "unit": "states/s", "seconds": time.time() - ts, "kernel_seconds": rs.seconds_kernels,
@@ -437,7 +444,7 @@ def main():
                                    "reachable set (BASELINE configs[1] = shipped VSR.cfg)",
                        "state_bytes": S, "distinct_states": res.distinct, "states_generated": res.generated, "depth": res.depth,
                        "first_violation_depth": res.violation_level, "parallelism": "fingerprint-sharded x%d" % world,
-                       "exchange": "none" if world == 1 else "expand_kernel stores each remote successor into the owner's inbox over NVLink "
+                       "exchange": "none" if world == 1 else "STAGED BASELINE: local staging buffer + NCCL send/recv per step, Python level loop" if staged else "expand_kernel stores each remote successor into the owner's inbox over NVLink "
                                    "(CUDA IPC peer mapping, TMA bulk store per destination run); the owner inserts it in its next launch; "
                                    "C++ level loop, shared-memory all-gather between ranks; NCCL only for the bench's own barrier/timing",
                        "l2": "working set (seen-set %.1f GiB per GPU) exceeds L2; no flush needed" % (table_cap * 16 / 2**30),
@@ -465,7 +472,7 @@ def main():
                          "kernel": "expand_kernel<Layout<3,2,3>> (per-GPU states x B_alg / sum of per-level kernel time, max over ranks)"},
             "e2e": ({"value": e2e_states / e2e_s, "unit": "states/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                      "seconds": e2e_s, "seconds_all_runs": e2e_runs,
-                     "api": "ModelChecker.from_cfg_text(cfg).check()" if world == 1 else "ModelChecker.from_cfg_text(cfg) + dist.GpuEngine(group=...).run() + replay_trace()"}
+                     "api": "ModelChecker.from_cfg_text(cfg).check()" if world == 1 else "dist.check_sharded(ModelChecker.from_cfg_text(cfg), group) on every rank"}
                     if e2e_s else None),
             "probe_roofline": probe,
             "clocks": clocks,
@@ -473,7 +480,7 @@ def main():
         if cfg3 is not None:
             out["cfg3_first_violation"] = cfg3
         if small_gpu is not None:
-            out["same_config_small"] = {"workload": "VSR.tla ReplicaCount=3 Values={v1,v2} StartViewOnTimerLimit=1, COMPLETE state space (%d distinct states, depth %d)"
+            out["same_config_small"] = {"workload": "VSR.tla ReplicaCount=3 Values={v1,v2} StartViewOnTimerLimit=1 VIEW view, no SYMMETRY: COMPLETE state space (%d distinct states, depth %d)"
                                                     % (SMALL["distinct"], SMALL["depth"]), "gpu": small_gpu}
         if world == 1 and not args.no_cpu_baseline:
             try:

@@ -85,9 +85,9 @@ def bfs(q, workers=4, max_depth=0, max_states=0, max_seconds=0.0, check_deadlock
     return OracleBfs(scal, [int(lv[i]) for i in range(n)], [int(lg[i]) for i in range(n)], level_digests, trace)
 
 
-def digests_of(q, flats):
-    """canonical VIEW digests (16 bytes each) + aux keys of an array of VsrFlatState"""
-    n = len(flats)
+def digests_of(q, flats, n=None):
+    """canonical VIEW digests (16 bytes each) + aux keys of (the first n of) an array of VsrFlatState"""
+    n = len(flats) if n is None else n
     out = (C.c_uint64 * (2 * n))()
     aux = (C.c_uint32 * n)()
     lib().orc_digest_flat(q, flats, n, out, aux)

@@ -17,23 +17,28 @@ pytestmark = pytest.mark.gpu
 def level_digest_sets(pkg, mc, res, q):
     sb = mc.state_bytes
     out = []
+    CH = 8192  # a VsrFlatState is 19 kB: unpack and digest wide levels in chunks
+    flats = (pkg.checker.VsrFlatState * CH)()
     for raw in res.levels:
         n = len(raw) // sb
-        flats = (pkg.checker.VsrFlatState * n)()
-        for i in range(n):
-            st = (C.c_uint8 * sb).from_buffer_copy(raw[i * sb:(i + 1) * sb])
-            rc = mc._lib.vsr_unpack(mc._h, st, C.byref(flats[i]))
-            assert rc == 0
-        digs, _ = orc.digests_of(q, flats)
-        assert len(set(digs)) == n, "GPU level holds two states with the same canonical VIEW"
-        out.append(set(digs))
+        digs = set()
+        for c0 in range(0, n, CH):
+            m = min(CH, n - c0)
+            buf = (C.c_uint8 * (m * sb)).from_buffer_copy(raw[c0 * sb:(c0 + m) * sb])
+            base = C.addressof(buf)
+            for i in range(m):
+                assert mc._lib.vsr_unpack(mc._h, base + i * sb, C.byref(flats[i])) == 0
+            d, _ = orc.digests_of(q, flats, m)
+            digs.update(d)
+        assert len(digs) == n, "GPU level holds two states with the same canonical VIEW"
+        out.append(digs)
     return out
 
 
-def run_pair(pkg, R, V, L, symmetry=True, max_depth=0, inv=("AcknowledgedWriteNotLost",), table=1 << 22, frontier=1 << 20):
+def run_pair(pkg, R, V, L, symmetry=True, max_depth=0, inv=("AcknowledgedWriteNotLost",), table=1 << 23, frontier=1 << 21, **check_kw):
     mc = pkg.ModelChecker.from_constants(R, V, L, symmetry=symmetry, invariants=inv)
     res = mc.check(collect_levels=True, max_depth=max_depth, table_capacity=table, frontier_capacity=frontier,
-                   stop_on_violation=False)
+                   stop_on_violation=False, **check_kw)
     inv_id = 1 if "AcknowledgedWriteNotLost" in inv else (2 if "AcknowledgedWritesExistOnMajority" in inv else 4)
     q = orc.params(R, V, L, symmetry=symmetry and V > 1, invariant=inv_id)
     o = orc.bfs(q, workers=8, max_depth=max_depth, keep_trace=False, digests=True)
@@ -73,9 +78,10 @@ def test_cfg1_scalars(pkg):
     assert (res.generated, res.distinct, res.queue, res.depth, res.rc, res.complete) == (100, 76, 0, 14, 0, True)
 
 
-@pytest.mark.parametrize("R,V,L,depth", [(3, 2, 2, 11), (3, 3, 3, 10), (5, 2, 2, 7), (3, 2, 1, 14), (4, 2, 2, 8), (3, 3, 2, 10)])
+@pytest.mark.parametrize("R,V,L,depth", [(3, 2, 2, 15), (3, 3, 3, 13), (5, 2, 2, 9), (3, 2, 1, 14), (4, 2, 2, 8), (3, 3, 2, 10)])
 def test_bounded_depth_matches_oracle(pkg, R, V, L, depth):
-    """cfg2 (shipped VSR.cfg), cfg3 (README), cfg4 (R=5) and friends, as deep as the oracle goes in seconds."""
+    """cfg2 (shipped VSR.cfg), cfg3 (README), cfg4 (R=5) and friends, as deep as the oracle goes in about a minute on eight
+    threads (1.1 - 1.7 million states each for the three BASELINE configs): every depth's SET of states equal."""
     mc, res, q, o = run_pair(pkg, R, V, L, max_depth=depth)
     assert_same_exploration(pkg, mc, res, q, o, complete=False)
     assert res.queue == res.level_sizes[-1]
@@ -249,6 +255,34 @@ def test_simulation_mode_walks_like_the_host_and_replays_violations(pkg):
     st2, trace2 = hook.simulate(num_walks=1 << 16, depth=40, seed=5)
     assert (st2.violating_walk, st2.violation_depth, st2.steps) == (st.violating_walk, st.violation_depth, st.steps)
     assert [s for _, s in trace2] == [s for _, s in trace]
+
+
+def test_frontier_spill_and_odd_capacities_give_the_same_exploration(pkg):
+    """BASELINE configs[3]'s capacity path at test size: 700 frontier states in HBM, the rest of every level in pinned host
+    memory (levels of up to thousands of states: most of them straddle the boundary), and a seen-set whose capacity is not a
+    power of two.  Same per-depth state SETS as the oracle."""
+    mc, res, q, o = run_pair(pkg, 3, 1, 1, table=100_000, frontier=700, frontier_host_capacity=1 << 16)
+    assert res.rc == 0 and res.table_capacity == 100_032 and res.frontier_capacity == 700 + (1 << 16)
+    assert max(res.level_sizes) > 2000
+    assert_same_exploration(pkg, mc, res, q, o, complete=True)
+    # without the host part the same run must stop with TLC's "state space too large", not lose states
+    small = mc.check(table_capacity=100_000, frontier_capacity=700, stop_on_violation=False)
+    assert small.rc == 152 and not small.complete
+
+
+def test_threads_of_one_process_shard_the_search(pkg, monkeypatch):
+    """vsr_bfs_multi (what `vsrmc -gpus N` runs): one thread per rank, inboxes reached through plain peer pointers.  On a
+    one-GPU box the test hook VSR_B200_MULTI_ONE_DEVICE puts every rank on device 0."""
+    monkeypatch.setenv("VSR_B200_MULTI_ONE_DEVICE", "1")
+    for world in (2, 4):
+        mc = pkg.ModelChecker.from_constants(3, 2, 1, invariants=("AcknowledgedWritesExistOnMajority",))
+        res = mc.check_multi(world, table_capacity=1 << 20, frontier_capacity=1 << 18)
+        o = orc.bfs(orc.params(3, 2, 1, invariant=2), workers=8, keep_trace=False, check_assumptions=False)
+        assert res.rc == 12 == o.rc and res.violation_level == o.depth and len(res.trace) == o.depth
+        assert res.violated_invariants == ["AcknowledgedWritesExistOnMajority"]
+        assert res.level_sizes == o.level_sizes
+        full = pkg.ModelChecker.from_constants(3, 2, 1, symmetry=False).check_multi(world, table_capacity=1 << 21, frontier_capacity=1 << 18, stop_on_violation=False)
+        assert (full.rc, full.complete, full.distinct, full.generated, full.depth) == (0, True, 697364, 1831657, 30)
 
 
 def test_shipped_cfg_full_size_properties(pkg):

@@ -62,7 +62,6 @@ def test_compile_failure_is_reported_not_hidden(pkg):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="first GPU run of a plug-in layout: written after the round's GPU budget was spent")
 def test_plugin_layout_full_state_space_on_the_gpu(pkg):
     """Complete BFS of (R=2, 4 values, limit 2) on the GPU through a plug-in layout, per-depth state sets against the
     oracle.  Runs in a child process: the plug-in's kernels have not been on a GPU yet, and a crash there must not

@@ -69,6 +69,7 @@ void fill_params(VsrEngine* e, ExpandParams& p) {
     p.owner_shift = e->owner_shift;
     p.send_count = e->send_count;
     p.push_cap = e->inbox_cap;
+    p.push_direct = e->push_direct;
 }
 
 extern "C" {
@@ -96,6 +97,7 @@ int vsr_engine_create(const VsrModel* m, const VsrRunOpts* opts, int rank, int w
     while ((1 << lg) < world) lg++;
     e->owner_shift = world > 1 ? 64 - lg : 64;
     e->device = opts->device;
+    if (const char* pm = getenv("VSR_B200_PUSH")) e->push_direct = strcmp(pm, "direct") == 0;
     memset(&e->st, 0, sizeof e->st);
     auto bail = [&](const char* what, cudaError_t c) {
         std::string msg = std::string(what) + ": " + cudaGetErrorString(c);
@@ -221,8 +223,8 @@ int vsr_engine_step(VsrEngine* e, uint64_t first, uint64_t count, int parity, co
         int rc = engine_reset_level(e);
         if (rc) return rc;
     }
-    if (first >= e->n_cur) count = 0;
-    if (first + count > e->n_cur) count = e->n_cur - first;
+    if (first >= e->n_cur) { first = e->n_cur; count = 0; } /* this rank's frontier ends before the part (or the launch only drains) */
+    else if (count > e->n_cur - first) count = e->n_cur - first;
     ExpandParams p;
     fill_params(e, p);
     if (first < p.in_split || !e->frontier_host_cap) {
@@ -412,9 +414,9 @@ int vsr_engine_finish_level(VsrEngine* e, VsrLevelInfo* out) {
     e->next_base += n_new;
     e->level = gen_level;
     e->level_open = false;
-    if (e->opts.collect_levels && n_new) {
+    if (e->opts.collect_levels) { /* one entry per level, empty when this rank found nothing at that depth (several ranks) */
         std::vector<uint8_t> host((size_t)n_new * e->g->bytes);
-        if (vsr_engine_read_frontier(e, 0, n_new, host.data())) return VSR_RC_SYSTEM;
+        if (n_new && vsr_engine_read_frontier(e, 0, n_new, host.data())) return VSR_RC_SYSTEM;
         e->collected.push_back(std::move(host));
     }
     if (out) *out = li;

@@ -96,6 +96,7 @@ struct ExpandParams {
        buffer when the host moves them with a collective.  Slots are taken from the local counters send_count[d]. */
     uint8_t* push[MAX_WORLD];
     unsigned long long push_cap; /* records per segment */
+    int push_direct;             /* 1: every lane stores its own record with 16-byte stores (VSR_B200_PUSH=direct); 0: staged + TMA bulk store */
     unsigned int* send_count;    /* MAX_WORLD counters, zeroed before every launch */
     /* records received from rank s in the previous step (the other half of the double-buffered inbox): inserted by this
        launch after its share of the frontier */
@@ -171,7 +172,7 @@ __device__ __forceinline__ uint64_t make_meta(int level, uint32_t auxkey, uint32
    are loaded by the caller as early as the fingerprint is known so that the HBM round trip overlaps the rest of the
    successor's work. */
 #ifndef VSR_BUCKET
-#define VSR_BUCKET 1
+#define VSR_BUCKET 2
 #endif
 struct Probe { uint64_t e[2 * VSR_BUCKET]; };
 __device__ __forceinline__ void ld256_cg(const uint64_t* p, uint64_t& a, uint64_t& b, uint64_t& c, uint64_t& d) {
@@ -390,6 +391,15 @@ template <class L> struct Expander {
         base = __shfl_sync(0xffffffffu, base, mymask ? __ffs(mymask) - 1 : 0);
         const bool fits = send_to >= 0 && (unsigned long long)base + (unsigned)cnt <= P.push_cap;
         if (send_to >= 0 && !fits && rnk == 0) atomicExch(&P.ctr->overflow, 3);
+        if (P.push_direct) { /* fallback / A-B: no staging, four half-sector stores per lane */
+            if (fits) {
+                uint4* d = reinterpret_cast<uint4*>(P.push[send_to] + (size_t)(base + (unsigned)rnk) * RB);
+                VSR_UNROLL
+                for (int q = 0; q < L::NW / 4; q++) d[q] = make_uint4(v.w[4 * q], v.w[4 * q + 1], v.w[4 * q + 2], v.w[4 * q + 3]);
+                d[L::NW / 4] = make_uint4((uint32_t)fp, (uint32_t)(fp >> 32), (uint32_t)tm, (uint32_t)(tm >> 32));
+            }
+            return;
+        }
         const int pos = off + rnk, total = __popc(senders);
         uint32_t* sbuf = &S.stage[32 * L::NW];
         for (int lo = 0; lo < total; lo += CAPREC) {

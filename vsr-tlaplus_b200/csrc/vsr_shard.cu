@@ -85,12 +85,13 @@ int vsr_engine_detach(VsrEngine* e) {
 }
 
 uint64_t vsr_engine_default_inbox_records(const VsrEngine* e) {
-    /* a step of S frontier states per rank pushes about S * (successors per state) * (world - 1) / world records, spread
-       over world - 1 peers; 1/16 of the frontier capacity per segment keeps the inbox (2 halves x world segments) at a
-       fraction of the frontier's memory and still gives steps of millions of states */
-    uint64_t cap = e->frontier_cap / 16;
+    /* a step of S frontier states per rank pushes about S * (successor records per state) * (world - 1) / world records,
+       spread over world - 1 peers.  1/8 of the frontier capacity per segment (at most 16 M records) keeps the inbox
+       (2 halves x world segments) at a fraction of the frontier's memory and gives steps of millions of states, so the
+       per-step host round trip (launch, 32-byte read-back, shared-memory all-gather: ~50 us) stays a few per cent */
+    uint64_t cap = e->frontier_cap / 8;
     if (cap < 4096) cap = 4096;
-    if (cap > (1ull << 26)) cap = 1ull << 26;
+    if (cap > (1ull << 24)) cap = 1ull << 24;
     return cap;
 }
 
@@ -376,8 +377,10 @@ int vsr_bfs_multi(const VsrModel* m, const VsrRunOpts* opts, int ngpus, uint64_t
         if (err && errcap) snprintf(err, errcap, "-gpus must be 1, 2, 4 or 8");
         return VSR_RC_CONFIG_ERROR;
     }
+    const char* one = getenv("VSR_B200_MULTI_ONE_DEVICE"); /* test hook: every rank on opts->device (a one-GPU box) */
+    const bool one_device = one && one[0] == '1';
     int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < opts->device + ngpus) {
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < opts->device + (one_device ? 1 : ngpus)) {
         if (err && errcap) snprintf(err, errcap, "%d GPUs requested from device %d on, %d visible: the BFS runs on GPUs only, there is no CPU fallback", ngpus, opts->device, ndev);
         return VSR_RC_SYSTEM;
     }
@@ -392,7 +395,7 @@ int vsr_bfs_multi(const VsrModel* m, const VsrRunOpts* opts, int ngpus, uint64_t
     for (int r = 0; r < ngpus; r++) {
         threads.emplace_back([&, r]() {
             VsrRunOpts o = *opts;
-            o.device = opts->device + r;
+            o.device = opts->device + (one_device ? 0 : r);
             char msg[256] = {0};
             VsrEngine* e = nullptr;
             int rc = vsr_engine_create(m, &o, r, ngpus, &e, msg, sizeof msg);

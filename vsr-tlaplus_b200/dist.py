@@ -112,6 +112,8 @@ class ShardedResult:
     # staged pump only: this rank's host wall clock by phase
     phase_seconds: dict = field(default_factory=lambda: {"expand": 0.0, "exchange": 0.0, "finish": 0.0})
     launches: int = 0
+    bytes_h2d: int = 0               # host<->device bytes this rank's engine moved (inputs, per-step counters, trace reads)
+    bytes_d2h: int = 0
     trace_cands: List[int] = field(default_factory=list)
     trace: List[Tuple[str, bytes]] = field(default_factory=list)
 
@@ -178,7 +180,7 @@ class GpuEngine:
                           violation_gid=int(st.violation_id) if st.violation_level else -1, seconds=float(st.seconds_total),
                           kernel_ms_max=float(st.seconds_kernels) * 1e3, insert_ms_max=float(st.seconds_insert) * 1e3,
                           exchanged_records=int(st.records_sent), received_records=int(st.records_received),
-                          launches=int(st.kernel_launches))
+                          launches=int(st.kernel_launches), bytes_h2d=int(st.bytes_h2d), bytes_d2h=int(st.bytes_d2h))
         if want_trace and (rc in (11, 12) or r.violation_level):
             r.trace_cands = [int(cands[i]) for i in range(int(n.value))]
         return r
