@@ -162,3 +162,14 @@ def test_init_has_the_hand_derivable_successors(pkg):
         assert len({t for t, _, _ in succ}) == (R - 1) + 1
         mc = pkg.ModelChecker.from_constants(R, V, L, symmetry=False)
         assert len({t for t, _, _ in mc.successors(mc.init_state())}) == (R - 1) + V
+
+
+def test_check_deadlock_keyword_of_the_cfg_is_honoured(pkg):
+    """CHECK_DEADLOCK FALSE in the cfg must switch deadlock checking off (TLC does), not be parsed and dropped."""
+    base = pkg.cfg_text(2, ["v1"], 1)
+    off = pkg.ModelChecker.from_cfg_text(base + "CHECK_DEADLOCK FALSE\n")
+    on = pkg.ModelChecker.from_cfg_text(base + "CHECK_DEADLOCK TRUE\n")
+    absent = pkg.ModelChecker.from_cfg_text(base)
+    assert (off.info.check_deadlock, on.info.check_deadlock, absent.info.check_deadlock) == (0, 1, -1)
+    assert off.run_opts().check_deadlock == 0 and on.run_opts().check_deadlock == 1 and absent.run_opts().check_deadlock == 0
+    assert off.run_opts(deadlock=True).check_deadlock == 1  # an explicit argument wins, like TLC's command line over the cfg

@@ -51,7 +51,6 @@ struct VsrEngine {
     uint64_t tie_cap = 0;
     uint64_t* fp_tab = nullptr;
     uint8_t* init_rec = nullptr;
-    unsigned int* send_count = nullptr;   /* MAX_WORLD counters (world > 1) */
     /* world > 1: the exchange.  inbox = 2 halves x world segments x inbox_cap records; half h, segment s holds what rank s
        pushed here in a step of parity h.  peer_inbox[d] = rank d's inbox as seen from this device (CUDA IPC mapping or a
        peer pointer of the same process); staged mode: stage = world segments of outgoing records a collective moves */

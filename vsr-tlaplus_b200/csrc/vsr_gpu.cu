@@ -5,6 +5,7 @@
  * one small counter read-back, swap frontiers.  Kernels: vsr_gpu.cuh.
  * There is NO CPU fallback: without a usable CUDA device every entry point returns 153.
  */
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -67,12 +68,13 @@ void fill_params(VsrEngine* e, ExpandParams& p) {
     p.rank = e->rank;
     p.world = e->world;
     p.owner_shift = e->owner_shift;
-    p.send_count = e->send_count;
     p.push_cap = e->inbox_cap;
     p.push_direct = e->push_direct;
 }
 
 extern "C" {
+
+int vsr_gpu_abi(void) { return vsr::gpu_abi_value(); } /* compared with a layout plug-in's vsr_plugin_abi() before it is used */
 
 int vsr_engine_create(const VsrModel* m, const VsrRunOpts* opts, int rank, int world, VsrEngine** out, char* err, size_t errcap) {
     auto fail = [&](int rc, const std::string& msg) {
@@ -148,7 +150,6 @@ int vsr_engine_create(const VsrModel* m, const VsrRunOpts* opts, int rank, int w
     if ((ce = cudaMallocAsync((void**)&e->ctr, sizeof(DevCounters), e->stream)) != cudaSuccess) return bail("cudaMalloc", ce);
     if ((ce = cudaMallocAsync((void**)&e->ties, e->tie_cap * (size_t)e->g->tie_bytes, e->stream)) != cudaSuccess) return bail("cudaMalloc", ce);
     if ((ce = cudaMallocAsync((void**)&e->fp_tab, 8 * 256 * 8, e->stream)) != cudaSuccess) return bail("cudaMalloc", ce);
-    if (world > 1 && (ce = cudaMallocAsync((void**)&e->send_count, sizeof(unsigned int) * MAX_WORLD, e->stream)) != cudaSuccess) return bail("cudaMalloc", ce);
     if ((ce = cudaMallocAsync((void**)&e->init_rec, e->g->rec_bytes, e->stream)) != cudaSuccess) return bail("cudaMalloc", ce);
     if ((ce = cudaMemcpyAsync(e->fp_tab, fp64_table(), 8 * 256 * 8, cudaMemcpyHostToDevice, e->stream)) != cudaSuccess) return bail("memcpy", ce);
     e->st.table_capacity = tcap;
@@ -173,7 +174,6 @@ void vsr_engine_destroy(VsrEngine* e) {
     if (e->stream) cudaFreeAsync(e->ties, e->stream); else cudaFree(e->ties);
     if (e->stream) cudaFreeAsync(e->fp_tab, e->stream); else cudaFree(e->fp_tab);
     if (e->stream) cudaFreeAsync(e->init_rec, e->stream); else cudaFree(e->init_rec);
-    if (e->stream) cudaFreeAsync(e->send_count, e->stream); else cudaFree(e->send_count);
     vsr_engine_detach(e);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -254,12 +254,10 @@ int vsr_engine_step(VsrEngine* e, uint64_t first, uint64_t count, int parity, co
             drain_total += n;
         }
         p.drain_total = drain_total;
-        CK(cudaMemsetAsync(e->send_count, 0, sizeof(unsigned int) * MAX_WORLD, e->stream));
     }
     if (sent_out) memset(sent_out, 0, sizeof(uint32_t) * e->world);
     if (count == 0 && drain_total == 0) return 0;
-    CK(cudaMemsetAsync(&e->ctr->work_next, 0, sizeof(unsigned long long), e->stream));
-    CK(cudaMemsetAsync(&e->ctr->drain_next, 0, sizeof(unsigned long long), e->stream));
+    CK(cudaMemsetAsync(&e->ctr->work_next, 0, sizeof(DevCounters) - offsetof(DevCounters, work_next), e->stream)); /* work_next, drain_next, send_count[] */
     const uint64_t spb = (uint64_t)e->g->states_per_block;
     uint64_t want_blocks = (count + spb - 1) / spb;
     const uint64_t drain_blocks = (drain_total + spb - 1) / spb;
@@ -272,7 +270,7 @@ int vsr_engine_step(VsrEngine* e, uint64_t first, uint64_t count, int parity, co
     CK(cudaEventRecord(e->ev1, e->stream));
     e->st.kernel_launches++;
     if (e->world > 1 && sent_out) {
-        CK(cudaMemcpyAsync(sent_out, e->send_count, sizeof(uint32_t) * e->world, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyAsync(sent_out, e->ctr->send_count, sizeof(uint32_t) * e->world, cudaMemcpyDeviceToHost, e->stream));
         e->st.bytes_d2h += sizeof(uint32_t) * e->world;
     }
     CK(cudaStreamSynchronize(e->stream)); /* the pushed records have landed (kernel completion) before the host tells anybody */

@@ -41,13 +41,15 @@ struct DevCounters {
     unsigned long long probes;      /* table entries inspected */
     unsigned long long viol_id;     /* smallest global id of a violating new state (~0 = none) */
     unsigned long long dead_id;     /* smallest global id of an expanded state without successors */
-    unsigned long long work_next;   /* next 32-state chunk to hand out */
     unsigned long long tie_count;   /* entries in the tie list */
-    unsigned long long drain_next;  /* next chunk of inbox records to hand out */
     int error;                      /* first E_* raised */
     int overflow;                   /* next frontier / send buffer / tie list full */
     int viol_which;                 /* mask bit of the violated invariant */
     int _pad;
+    /* per LAUNCH (one memset clears them): */
+    unsigned long long work_next;   /* next round of frontier states to hand out */
+    unsigned long long drain_next;  /* next chunk of inbox records to hand out */
+    unsigned int send_count[8];     /* records pushed to each rank by this launch (MAX_WORLD) */
 };
 
 /* a same-level VIEW tie: header, then the candidate's L::NW packed words */
@@ -93,11 +95,10 @@ struct ExpandParams {
     int rank, world, owner_shift;/* owner(fp) = fp >> owner_shift (world a power of two; 64 when world = 1) */
     /* world > 1.  push[d] = where THIS rank's records for rank d go: its segment of rank d's inbox, in rank d's memory,
        mapped here over NVLink (CUDA IPC / peer access) — the expand kernel stores them there itself — or a local staging
-       buffer when the host moves them with a collective.  Slots are taken from the local counters send_count[d]. */
+       buffer when the host moves them with a collective.  Slots are taken from the local counters ctr->send_count[d]. */
     uint8_t* push[MAX_WORLD];
     unsigned long long push_cap; /* records per segment */
     int push_direct;             /* 1: every lane stores its own record with 16-byte stores (VSR_B200_PUSH=direct); 0: staged + TMA bulk store */
-    unsigned int* send_count;    /* MAX_WORLD counters, zeroed before every launch */
     /* records received from rank s in the previous step (the other half of the double-buffered inbox): inserted by this
        launch after its share of the frontier */
     const uint8_t* drain[MAX_WORLD];
@@ -387,7 +388,7 @@ template <class L> struct Expander {
             if (send_to == d) { mymask = m; cnt = __popc(m); rnk = __popc(m & ((1u << lane) - 1u)); }
         }
         unsigned base = 0;
-        if (send_to >= 0 && rnk == 0) base = atomicAdd(&P.send_count[send_to], (unsigned)cnt);
+        if (send_to >= 0 && rnk == 0) base = atomicAdd(&P.ctr->send_count[send_to], (unsigned)cnt);
         base = __shfl_sync(0xffffffffu, base, mymask ? __ffs(mymask) - 1 : 0);
         const bool fits = send_to >= 0 && (unsigned long long)base + (unsigned)cnt <= P.push_cap;
         if (send_to >= 0 && !fits && rnk == 0) atomicExch(&P.ctr->overflow, 3);
@@ -521,45 +522,74 @@ template <class L> struct Expander {
         return commit(P, S, lane, v, live, fp, chk, auxkey, home, first, trec, (unsigned)mult);
     }
 
-    /* ---- drain: one record received from a peer per lane (world > 1).  The sender computed the fingerprint; check hash
-       and aux key are recomputed from the words; then the same seen-set insert / invariant / staging as a local successor */
+    /* ---- drain: records received from peers (world > 1), DRAIN_U per lane and iteration.  The sender computed the
+       fingerprint; check hash and aux key are recomputed from the words; then the same seen-set insert / invariant /
+       staging as a local successor.  The drain is nothing but dependent memory round trips (header -> bucket -> CAS) at
+       the expand kernel's occupancy, so every lane keeps DRAIN_U independent probes in flight: all headers are loaded,
+       then all buckets, then the states, and only then the first record is committed. */
+#ifndef VSR_DRAIN_U
+#define VSR_DRAIN_U 2
+#endif
+    static constexpr int DRAIN_U = VSR_DRAIN_U;
     __device__ __forceinline__ void drain_chunk(unsigned long long firstrec) {
         constexpr int RB = L::BYTES + (int)sizeof(RecHdr);
-        unsigned long long i = firstrec + lane;
-        const bool have = i < P.drain_total;
-        RegRow<L::NW> v;
-        uint64_t fp = 0, tm = 0;
-        uint32_t chk = 0, auxkey = 0;
-        unsigned long long home = 0;
-        Probe first = {};
-        if (have) {
-            int s = 0;
-            while (s < P.world - 1 && i >= P.drain_n[s]) { i -= P.drain_n[s]; s++; }
-            const uint4* r = reinterpret_cast<const uint4*>(P.drain[s] + i * RB);
-            const uint4 h = __ldcs(r + L::NW / 4);
-            fp = ((uint64_t)h.y << 32) | h.x;
-            tm = ((uint64_t)h.w << 32) | h.z;
-            home = table_home(P.table_cap, fp);
-            probe_load(P.table, home, first);
-            VSR_UNROLL
-            for (int q = 0; q < L::NW / 4; q++) {
-                const uint4 x = __ldcs(r + q);
-                v.w[4 * q] = x.x; v.w[4 * q + 1] = x.y; v.w[4 * q + 2] = x.z; v.w[4 * q + 3] = x.w;
+        RegRow<L::NW> v[DRAIN_U];
+        uint64_t fp[DRAIN_U], tm[DRAIN_U];
+        unsigned long long home[DRAIN_U];
+        Probe first[DRAIN_U];
+        const uint4* rec[DRAIN_U];
+        bool have[DRAIN_U];
+VSR_UNROLL
+        for (int u = 0; u < DRAIN_U; u++) {
+            unsigned long long i = firstrec + u * 32 + lane;
+            have[u] = i < P.drain_total;
+            fp[u] = tm[u] = 0;
+            home[u] = 0;
+            first[u] = Probe{};
+            rec[u] = nullptr;
+            if (have[u]) {
+                int s = 0;
+                while (s < P.world - 1 && i >= P.drain_n[s]) { i -= P.drain_n[s]; s++; }
+                rec[u] = reinterpret_cast<const uint4*>(P.drain[s] + i * RB);
+                const uint4 h = __ldcs(rec[u] + L::NW / 4);
+                fp[u] = ((uint64_t)h.y << 32) | h.x;
+                tm[u] = ((uint64_t)h.w << 32) | h.z;
             }
-            chk = check_hash<L>(v, P.run.use_view != 0);
-            auxkey = O_::aux_key(v);
         }
-        tally(commit(P, S, lane, v, have, fp, chk, auxkey, home, first, tm & ((1ull << 56) - 1ull), (unsigned)((tm >> 56) & 0xFu)));
+VSR_UNROLL
+        for (int u = 0; u < DRAIN_U; u++)
+            if (have[u]) {
+                home[u] = table_home(P.table_cap, fp[u]);
+                probe_load(P.table, home[u], first[u]);
+            }
+VSR_UNROLL
+        for (int u = 0; u < DRAIN_U; u++)
+            if (have[u]) {
+                VSR_UNROLL
+                for (int q = 0; q < L::NW / 4; q++) {
+                    const uint4 x = __ldcs(rec[u] + q);
+                    v[u].w[4 * q] = x.x; v[u].w[4 * q + 1] = x.y; v[u].w[4 * q + 2] = x.z; v[u].w[4 * q + 3] = x.w;
+                }
+            }
+VSR_UNROLL
+        for (int u = 0; u < DRAIN_U; u++) {
+            uint32_t chk = 0, auxkey = 0;
+            if (have[u]) {
+                chk = check_hash<L>(v[u], P.run.use_view != 0);
+                auxkey = O_::aux_key(v[u]);
+            }
+            tally(commit(P, S, lane, v[u], have[u], fp[u], chk, auxkey, home[u], first[u], tm[u] & ((1ull << 56) - 1ull), (unsigned)((tm[u] >> 56) & 0xFu)));
+        }
     }
     __device__ void drain() {
-        const unsigned long long nchunks = (P.drain_total + 31) / 32;
+        const unsigned long long nchunks = (P.drain_total + 32 * DRAIN_U - 1) / (32 * DRAIN_U);
         unsigned long long c = 0;
         if (lane == 0) c = atomicAdd(&P.ctr->drain_next, 1ull);
         c = __shfl_sync(0xffffffffu, c, 0);
         while (c < nchunks) {
             unsigned long long nx = 0;
             if (lane == 0) nx = atomicAdd(&P.ctr->drain_next, 1ull); /* the next claim's latency hides under this chunk */
-            drain_chunk(c * 32);
+            drain_chunk(c * 32 * DRAIN_U);
             c = __shfl_sync(0xffffffffu, nx, 0);
         }
     }

@@ -6,6 +6,7 @@
 #define VSR_GPU_THUNKS_CUH
 
 #include "vsr_gpu.cuh"
+#include "vsr_model.h"
 
 namespace vsr {
 
@@ -21,6 +22,12 @@ struct GpuOps {
     cudaError_t (*prepare)(int* blocks_per_sm);
     cudaError_t (*launch_simulate)(const SimParams&, int grid, cudaStream_t);
 };
+
+/* what a layout plug-in must have been compiled against: the version constant AND the shapes of the structs the kernels and the
+   host exchange (a plug-in built from another revision of these headers must be rebuilt, never loaded) */
+inline int gpu_abi_value() {
+    return VSR_PLUGIN_ABI * 100000 + (int)((sizeof(ExpandParams) * 131 + sizeof(DevCounters) * 17 + sizeof(InsertParams) * 7 + sizeof(RecHdr) + VSR_BUCKET * 3) % 100000);
+}
 
 template <class L> struct GpuThunks {
     static cudaError_t prepare(int* blocks_per_sm) {

@@ -69,7 +69,7 @@ static bool try_open_plugin(const std::string& path, int R, int V, int K, Layout
     abi_fn abi = (abi_fn)dlsym(h, "vsr_plugin_abi");
     ops_fn ops = (ops_fn)dlsym(h, "vsr_plugin_model_ops");
     gpu_fn gpu = (gpu_fn)dlsym(h, "vsr_plugin_gpu_ops");
-    if (!abi || !ops || !gpu || abi() != VSR_PLUGIN_ABI) {
+    if (!abi || !ops || !gpu || abi() != vsr_gpu_abi()) {
         why = "built against another version of the library";
         dlclose(h);
         return false;

@@ -21,7 +21,7 @@ static_assert(VSR_ONLY_R <= VSR_MAX_R && VSR_ONLY_V <= VSR_MAX_V, "beyond the fl
 static_assert(sizeof(vsr::ExpandCfg<PluginLayout>::Smem) <= 227 * 1024, "expand kernel's shared memory exceeds an SM");
 
 extern "C" {
-int vsr_plugin_abi(void) { return VSR_PLUGIN_ABI; }
+int vsr_plugin_abi(void) { return vsr::gpu_abi_value(); }
 const vsr::ModelOps* vsr_plugin_model_ops(void) { return vsr::Thunks<PluginLayout>::get(); }
 const vsr::GpuOps* vsr_plugin_gpu_ops(void) { return vsr::GpuThunks<PluginLayout>::get(); }
 }

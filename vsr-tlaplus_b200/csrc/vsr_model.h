@@ -48,6 +48,8 @@ const GpuOps* find_gpu_ops(int R, int V, int K); /* defined in vsr_gpu.cu */
 
 } // namespace vsr
 
+extern "C" int vsr_gpu_abi(void); /* vsr_gpu.cu: version + shapes of the kernel parameter structs */
+
 struct VsrModel {
     VsrModelInfo info;
     vsr::RunCfg run;
