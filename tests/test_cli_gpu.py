@@ -11,10 +11,11 @@ pytestmark = pytest.mark.gpu
 VSRMC = os.path.join(ROOT, "vsr-tlaplus_b200", "vsrmc")
 
 
-def run(args, tmp_path, cfg):
+def run(args, tmp_path, cfg, env=None):
     p = tmp_path / "m.cfg"
     p.write_text(cfg)
-    r = subprocess.run([VSRMC, "-config", str(p), "-table", "1048576", "-frontier", "200000"] + args, capture_output=True, text=True, timeout=300)
+    r = subprocess.run([VSRMC, "-config", str(p), "-table", "1048576", "-frontier", "200000"] + args, capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, **(env or {})))
     return r.returncode, r.stdout + r.stderr
 
 
@@ -49,3 +50,24 @@ def test_cli_violation_exit_12_and_dumptrace(pkg, tmp_path):
 def test_cli_depth_bound(pkg, tmp_path):
     rc, out = run(["-deadlock", "-depth", "5"], tmp_path, pkg.cfg_text(3, ["v1", "v2"], 2))
     assert rc == 0 and "The depth of the state graph search so far is 5." in out and "173 distinct states found" in out
+
+
+def test_cli_gpus_flag_shards_the_search_and_names_the_violated_invariant(pkg, tmp_path):
+    """`-gpus N` (TLC's -workers, here: fingerprint-sharded GPUs).  On a one-GPU box the test hook puts the ranks on device 0.
+    Two invariants configured, the SECOND one fails: the message must name that one."""
+    cfg = pkg.cfg_text(3, ["v1", "v2"], 1, invariants=["AcknowledgedWriteNotLost", "AcknowledgedWritesExistOnMajority"])
+    one = {"VSR_B200_MULTI_ONE_DEVICE": "1"}
+    rc1, out1 = run(["-deadlock"], tmp_path, cfg)
+    rc4, out4 = run(["-deadlock", "-gpus", "4"], tmp_path, cfg, env=one)
+    assert rc1 == rc4 == 12
+    for out in (out1, out4):
+        assert "Error: Invariant AcknowledgedWritesExistOnMajority is violated." in out
+        assert "Invariant AcknowledgedWriteNotLost is violated" not in out
+    assert "on GPUs 0..3" in out4
+    line = [ln for ln in out1.splitlines() if "distinct states found" in ln]
+    assert line and line == [ln for ln in out4.splitlines() if "distinct states found" in ln]
+
+
+def test_cli_honours_check_deadlock_false_in_the_cfg(pkg, tmp_path):
+    rc, out = run([], tmp_path, pkg.cfg_text(2, ["v1"], 1) + "CHECK_DEADLOCK FALSE\n")
+    assert rc == 0 and "Model checking completed. No error has been found." in out

@@ -24,7 +24,6 @@ build() { # name, flags
 build base ""
 build bucket1 "-DVSR_BUCKET=1"           # seen-set probe = one 128-bit load of one entry (round 1); default is the 2-entry sector bucket
 build bucket4 "-DVSR_BUCKET=4"           # 4-entry bucket, two 256-bit loads issued together
-build drain1 "-DVSR_DRAIN_U=1"           # records per lane in flight in the drain of the inbox (several GPUs): 1, 2 (default), 4
-build drain4 "-DVSR_DRAIN_U=4"
+
 build qps1 "-DVSR_QPS=1"                 # correctness variant (pool overflow path): VSR_B200_LIB=...qps1.so python -m pytest tests/test_gpu_parity.py -k "3-2-2 or deterministic"
 rm -f $OUT/vsr_group.o

@@ -296,7 +296,9 @@ template <class L> struct ExpandCfg {
  * run-time loop over candidates with one ballot + barrier per group: 75 warp instructions per (32 states, candidate)
  * for slot decoding and shared-memory field reads; (3) this form: 16 per candidate, 46 % fewer instructions overall.
  */
-template <class L> struct Expander {
+/* MULTI: the instantiation for several GPUs (push_records in emit, drain after the rounds).  The one-GPU instantiation has none
+   of that code: it costs the hot path registers (380 vs 140 bytes of spills in emit at the 64-register budget). */
+template <class L, bool MULTI> struct Expander {
     typedef Ops<L> O_;
     typedef typename ExpandCfg<L>::Smem Smem;
     static constexpr int WARPS = ExpandCfg<L>::WARPS, NS = Smem::NS;
@@ -515,82 +517,77 @@ template <class L> struct Expander {
                 }
             }
         }
-        if (P.world > 1) {
+        if (MULTI) {
             __syncwarp(); /* every lane has read its scratch row: that half of the staging area may now carry outgoing records */
             push_records(P, S, lane, v, send_to, fp, trec | ((uint64_t)(unsigned)mult << 56));
         }
         return commit(P, S, lane, v, live, fp, chk, auxkey, home, first, trec, (unsigned)mult);
     }
 
-    /* ---- drain: records received from peers (world > 1), DRAIN_U per lane and iteration.  The sender computed the
-       fingerprint; check hash and aux key are recomputed from the words; then the same seen-set insert / invariant /
-       staging as a local successor.  The drain is nothing but dependent memory round trips (header -> bucket -> CAS) at
-       the expand kernel's occupancy, so every lane keeps DRAIN_U independent probes in flight: all headers are loaded,
-       then all buckets, then the states, and only then the first record is committed. */
-#ifndef VSR_DRAIN_U
-#define VSR_DRAIN_U 2
-#endif
-    static constexpr int DRAIN_U = VSR_DRAIN_U;
-    __device__ __forceinline__ void drain_chunk(unsigned long long firstrec) {
-        constexpr int RB = L::BYTES + (int)sizeof(RecHdr);
-        RegRow<L::NW> v[DRAIN_U];
-        uint64_t fp[DRAIN_U], tm[DRAIN_U];
-        unsigned long long home[DRAIN_U];
-        Probe first[DRAIN_U];
-        const uint4* rec[DRAIN_U];
-        bool have[DRAIN_U];
-VSR_UNROLL
-        for (int u = 0; u < DRAIN_U; u++) {
-            unsigned long long i = firstrec + u * 32 + lane;
-            have[u] = i < P.drain_total;
-            fp[u] = tm[u] = 0;
-            home[u] = 0;
-            first[u] = Probe{};
-            rec[u] = nullptr;
-            if (have[u]) {
-                int s = 0;
-                while (s < P.world - 1 && i >= P.drain_n[s]) { i -= P.drain_n[s]; s++; }
-                rec[u] = reinterpret_cast<const uint4*>(P.drain[s] + i * RB);
-                const uint4 h = __ldcs(rec[u] + L::NW / 4);
-                fp[u] = ((uint64_t)h.y << 32) | h.x;
-                tm[u] = ((uint64_t)h.w << 32) | h.z;
-            }
-        }
-VSR_UNROLL
-        for (int u = 0; u < DRAIN_U; u++)
-            if (have[u]) {
-                home[u] = table_home(P.table_cap, fp[u]);
-                probe_load(P.table, home[u], first[u]);
-            }
-VSR_UNROLL
-        for (int u = 0; u < DRAIN_U; u++)
-            if (have[u]) {
-                VSR_UNROLL
-                for (int q = 0; q < L::NW / 4; q++) {
-                    const uint4 x = __ldcs(rec[u] + q);
-                    v[u].w[4 * q] = x.x; v[u].w[4 * q + 1] = x.y; v[u].w[4 * q + 2] = x.z; v[u].w[4 * q + 3] = x.w;
-                }
-            }
-VSR_UNROLL
-        for (int u = 0; u < DRAIN_U; u++) {
-            uint32_t chk = 0, auxkey = 0;
-            if (have[u]) {
-                chk = check_hash<L>(v[u], P.run.use_view != 0);
-                auxkey = O_::aux_key(v[u]);
-            }
-            tally(commit(P, S, lane, v[u], have[u], fp[u], chk, auxkey, home[u], first[u], tm[u] & ((1ull << 56) - 1ull), (unsigned)((tm[u] >> 56) & 0xFu)));
-        }
-    }
-    __device__ void drain() {
-        const unsigned long long nchunks = (P.drain_total + 32 * DRAIN_U - 1) / (32 * DRAIN_U);
+    /* ---- drain: one record received from a peer per lane (world > 1), after this block's share of the frontier.  The
+       sender computed the fingerprint; check hash and aux key are recomputed from the words; then the same seen-set insert
+       / invariant / staging as a local successor.  drain_begin issues the header and bucket loads, drain_end consumes them.
+       Measured (tools/drain_bench.py, profiles/round2_multi_gpu.md): push + drain cost 53 ps per record, i.e. the drain
+       runs close to the seen-set's random-access ceiling; what did NOT help: 2 or 4 records in flight per lane (+15 % /
+       +60 %: register spills), and pipelining a chunk under every batch of the expansion (+19 %, and +5 % on ONE GPU,
+       again through spills in the hot loop). */
+    struct DrainPre {
+        uint64_t fp, tm;
+        unsigned long long home;
+        Probe first;
+        const uint4* rec;
+        bool have;
+    };
+    unsigned long long dchunk = ~0ull; /* inbox chunk this warp has claimed (>= nchunks: none left) */
+    __device__ __forceinline__ unsigned long long drain_chunks() const { return (P.drain_total + 31) / 32; }
+    __device__ __forceinline__ unsigned long long drain_claim() {
         unsigned long long c = 0;
         if (lane == 0) c = atomicAdd(&P.ctr->drain_next, 1ull);
-        c = __shfl_sync(0xffffffffu, c, 0);
-        while (c < nchunks) {
-            unsigned long long nx = 0;
-            if (lane == 0) nx = atomicAdd(&P.ctr->drain_next, 1ull); /* the next claim's latency hides under this chunk */
-            drain_chunk(c * 32 * DRAIN_U);
-            c = __shfl_sync(0xffffffffu, nx, 0);
+        return c; /* lane 0's value; broadcast by the caller when it is needed (the atomic's latency hides under other work) */
+    }
+    __device__ __forceinline__ DrainPre drain_begin(unsigned long long chunk) {
+        constexpr int RB = L::BYTES + (int)sizeof(RecHdr);
+        DrainPre d;
+        unsigned long long i = chunk * 32 + lane;
+        d.have = chunk < drain_chunks() && i < P.drain_total;
+        d.fp = d.tm = 0;
+        d.home = 0;
+        d.first = Probe{};
+        d.rec = nullptr;
+        if (d.have) {
+            int s = 0;
+            while (s < P.world - 1 && i >= P.drain_n[s]) { i -= P.drain_n[s]; s++; }
+            d.rec = reinterpret_cast<const uint4*>(P.drain[s] + i * RB);
+            const uint4 h = __ldcs(d.rec + L::NW / 4);
+            d.fp = ((uint64_t)h.y << 32) | h.x;
+            d.tm = ((uint64_t)h.w << 32) | h.z;
+            d.home = table_home(P.table_cap, d.fp);
+            probe_load(P.table, d.home, d.first);
+        }
+        return d;
+    }
+    __device__ __forceinline__ void drain_end(const DrainPre& d) {
+        RegRow<L::NW> v;
+        uint32_t chk = 0, auxkey = 0;
+        if (d.have) {
+            VSR_UNROLL
+            for (int q = 0; q < L::NW / 4; q++) {
+                const uint4 x = __ldcs(d.rec + q);
+                v.w[4 * q] = x.x; v.w[4 * q + 1] = x.y; v.w[4 * q + 2] = x.z; v.w[4 * q + 3] = x.w;
+            }
+            chk = check_hash<L>(v, P.run.use_view != 0);
+            auxkey = O_::aux_key(v);
+        }
+        tally(commit(P, S, lane, v, d.have, d.fp, chk, auxkey, d.home, d.first, d.tm & ((1ull << 56) - 1ull), (unsigned)((d.tm >> 56) & 0xFu)));
+    }
+    __device__ void drain() {
+        const unsigned long long nchunks = drain_chunks();
+        if (dchunk == ~0ull) dchunk = __shfl_sync(0xffffffffu, drain_claim(), 0);
+        while (dchunk < nchunks) {
+            const unsigned long long nx = drain_claim(); /* the next claim's latency hides under this chunk */
+            const DrainPre d = drain_begin(dchunk);
+            drain_end(d);
+            dchunk = __shfl_sync(0xffffffffu, nx, 0);
         }
     }
 
@@ -799,13 +796,13 @@ VSR_UNROLL
     }
 };
 
-template <class L> __global__ void __launch_bounds__(ExpandCfg<L>::WARPS * 32, 2) expand_kernel(const __grid_constant__ ExpandParams P) {
+template <class L, bool MULTI> __global__ void __launch_bounds__(ExpandCfg<L>::WARPS * 32, 2) expand_kernel(const __grid_constant__ ExpandParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     typedef typename ExpandCfg<L>::Smem Smem;
     Smem& B = *reinterpret_cast<Smem*>(smem_raw);
     for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) B.fp_tab[i] = P.fp_tab[i];
     __shared__ unsigned long long next_round;
-    Expander<L> X(P, B);
+    Expander<L, MULTI> X(P, B);
     if ((threadIdx.x & 31) == 0) {
         WarpStage<L>& S = B.w[threadIdx.x >> 5];
         S.sn = 0;
@@ -832,7 +829,7 @@ template <class L> __global__ void __launch_bounds__(ExpandCfg<L>::WARPS * 32, 2
         const int count = (int)((P.n_in - first) < (unsigned long long)Smem::NS ? (P.n_in - first) : Smem::NS);
         X.run_round(first, count);
     }
-    if (P.drain_total) X.drain();
+    if (MULTI && P.drain_total) X.drain();
     X.finish();
 }
 

@@ -31,12 +31,18 @@ inline int gpu_abi_value() {
 
 template <class L> struct GpuThunks {
     static cudaError_t prepare(int* blocks_per_sm) {
-        cudaError_t e = cudaFuncSetAttribute(expand_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(typename ExpandCfg<L>::Smem));
+        cudaError_t e = cudaFuncSetAttribute(expand_kernel<L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(typename ExpandCfg<L>::Smem));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(expand_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(typename ExpandCfg<L>::Smem));
         if (e != cudaSuccess) return e;
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, expand_kernel<L>, ExpandCfg<L>::WARPS * 32, sizeof(typename ExpandCfg<L>::Smem));
+        int a = 0, b = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, expand_kernel<L, false>, ExpandCfg<L>::WARPS * 32, sizeof(typename ExpandCfg<L>::Smem));
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, expand_kernel<L, true>, ExpandCfg<L>::WARPS * 32, sizeof(typename ExpandCfg<L>::Smem));
+        *blocks_per_sm = a < b ? a : b;
+        return e;
     }
     static cudaError_t launch_expand(const ExpandParams& p, int grid, cudaStream_t st) {
-        expand_kernel<L><<<grid, ExpandCfg<L>::WARPS * 32, sizeof(typename ExpandCfg<L>::Smem), st>>>(p);
+        if (p.world > 1) expand_kernel<L, true><<<grid, ExpandCfg<L>::WARPS * 32, sizeof(typename ExpandCfg<L>::Smem), st>>>(p);
+        else expand_kernel<L, false><<<grid, ExpandCfg<L>::WARPS * 32, sizeof(typename ExpandCfg<L>::Smem), st>>>(p);
         return cudaGetLastError();
     }
     static cudaError_t launch_insert(const InsertParams& q, cudaStream_t st) {
