@@ -114,7 +114,14 @@ typedef struct VsrRunOpts {
        its frontier_capacity states in HBM, with this many states in pinned host memory mapped into the device; the kernels
        write and read that part over PCIe / C2C.  0 = no spill: a level that does not fit is a 152. */
     uint64_t frontier_host_capacity;
-    int32_t _reserved[4];
+    /* checkpoint / recover: TLC's `-checkpoint <minutes>` and `-recover <dir>` (the reference's .gitignore:1 ignores TLC's
+       states/ metadir, i.e. its users run with checkpoints).  checkpoint_path: file written at the first level boundary after
+       checkpoint_seconds since the last one (0 = after every level; written to <path>.tmp and renamed, so an interrupted write
+       leaves the previous checkpoint intact); recover_path: continue the BFS from that file instead of Init.  With several
+       ranks every rank uses <path>.rank<r>.  NULL = off. */
+    const char* checkpoint_path;
+    const char* recover_path;
+    double checkpoint_seconds;
 } VsrRunOpts;
 
 #define VSR_MAX_LEVELS 512
@@ -195,6 +202,13 @@ int vsr_engine_stats(const VsrEngine* e, VsrStats* out);
 /* membership query: *level_out = BFS depth at which `state` (a canonical packed state) was first seen, 0 if it is not
  * in this rank's shard of the seen-set; *owner_out = the rank owning its fingerprint */
 int vsr_engine_lookup(VsrEngine* e, const void* state, int* level_out, int* owner_out);
+/* Checkpoint of this rank's shard at a level boundary (after vsr_engine_finish_level, before the next expansion): the
+ * current frontier, every seen-set entry {fingerprint, meta}, the trace records and the run's statistics, to one file.
+ * vsr_engine_recover loads it into a fresh (or reset) engine of the same model, rank and world; the seen-set is re-inserted
+ * entry by entry, so its capacity may differ from the one the checkpoint was written with.  `totals` (may be NULL) travels
+ * with the file: vsr_bfs / vsr_bfs_sharded store the job's running totals there.  150 = not a checkpoint of this model. */
+int vsr_engine_checkpoint(VsrEngine* e, const char* path, const VsrStats* totals);
+int vsr_engine_recover(VsrEngine* e, const char* path, VsrStats* totals_out);
 /* forget everything explored (clears the seen-set, keeps the allocations): ready for seed_init again */
 int vsr_engine_reset(VsrEngine* e);
 const char* vsr_engine_last_error(const VsrEngine* e);

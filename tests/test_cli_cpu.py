@@ -27,7 +27,7 @@ def test_tlc_housekeeping_flags_are_accepted(pkg, tmp_path):
 
 
 def test_modes_that_do_not_exist_are_refused_by_name(pkg, tmp_path):
-    for flag in (["-recover", str(tmp_path)], ["-dfid", "10"]):
+    for flag in (["-dfid", "10"], ["-generateSpecTE"]):
         rc, out = run(["-deadlock"] + flag, tmp_path, pkg.cfg_text(2, ["v1"], 1))
         assert rc == 255 and flag[0] + " is not available" in out
     rc, out = run(["-bogus"], tmp_path, pkg.cfg_text(2, ["v1"], 1))

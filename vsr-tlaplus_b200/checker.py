@@ -96,7 +96,8 @@ class VsrRunOpts(C.Structure):
         ("stop_on_violation", C.c_int32), ("keep_trace", C.c_int32), ("verbose", C.c_int32),
         ("table_capacity", C.c_uint64), ("frontier_capacity", C.c_uint64), ("max_states", C.c_uint64),
         ("max_seconds", C.c_double), ("collect_levels", C.c_int32), ("_reserved0", C.c_int32),
-        ("frontier_host_capacity", C.c_uint64), ("_reserved", C.c_int32 * 4),
+        ("frontier_host_capacity", C.c_uint64), ("checkpoint_path", C.c_char_p), ("recover_path", C.c_char_p),
+        ("checkpoint_seconds", C.c_double),
     ]
 
 
@@ -144,7 +145,7 @@ EXPORTED_SYMBOLS = [
     "vsr_flat_to_tla", "vsr_action_name", "vsr_action_location", "vsr_bfs", "vsr_engine_create", "vsr_engine_destroy",
     "vsr_engine_record_bytes", "vsr_engine_seed_init", "vsr_engine_expand", "vsr_engine_expand_part", "vsr_engine_step",
     "vsr_engine_insert_records", "vsr_engine_finish_level", "vsr_engine_frontier_size", "vsr_engine_read_frontier",
-    "vsr_engine_trace_record", "vsr_engine_stats", "vsr_engine_reset", "vsr_engine_lookup", "vsr_engine_last_error", "vsr_engine_collected", "vsr_engine_build_trace",
+    "vsr_engine_trace_record", "vsr_engine_stats", "vsr_engine_reset", "vsr_engine_checkpoint", "vsr_engine_recover", "vsr_engine_lookup", "vsr_engine_last_error", "vsr_engine_collected", "vsr_engine_build_trace",
     "vsr_replay_candidates", "vsr_probe_bench", "vsr_simulate", "vsr_walk", "vsr_version",
     "vsr_group_open", "vsr_group_open_local", "vsr_group_close", "vsr_group_barrier", "vsr_group_allgather", "vsr_group_abort",
     "vsr_group_set_timeout", "vsr_group_rank", "vsr_group_world", "vsr_group_last_error",
@@ -224,6 +225,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.vsr_engine_trace_record.argtypes = [vp, u64, C.POINTER(u64), C.POINTER(C.c_uint32)]
     lib.vsr_engine_stats.argtypes = [vp, C.POINTER(VsrStats)]
     lib.vsr_engine_reset.argtypes = [vp]
+    lib.vsr_engine_checkpoint.argtypes = [vp, cp, C.POINTER(VsrStats)]
+    lib.vsr_engine_recover.argtypes = [vp, cp, C.POINTER(VsrStats)]
     lib.vsr_engine_lookup.argtypes = [vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.vsr_engine_last_error.argtypes = [vp]
     lib.vsr_engine_last_error.restype = cp
@@ -442,7 +445,10 @@ class ModelChecker:
     def run_opts(self, deadlock: Optional[bool] = None, max_depth: int = 0, device: int = 0, table_capacity: int = 0,
                  frontier_capacity: int = 0, keep_trace: bool = True, collect_levels: bool = False, max_states: int = 0,
                  max_seconds: float = 0.0, stop_on_violation: bool = True, verbose: bool = False,
-                 frontier_host_capacity: int = 0) -> VsrRunOpts:
+                 frontier_host_capacity: int = 0, checkpoint_path: Optional[str] = None, recover_path: Optional[str] = None,
+                 checkpoint_seconds: float = 0.0) -> VsrRunOpts:
+        """checkpoint_path / recover_path / checkpoint_seconds: TLC's -checkpoint / -recover (a file per rank at level
+        boundaries; see include/vsr_b200.h VsrRunOpts)"""
         o = VsrRunOpts()
         o.device = device
         if deadlock is None:  # CHECK_DEADLOCK of the cfg when it has one; otherwise off (VSR.tla has terminal states)
@@ -458,6 +464,9 @@ class ModelChecker:
         o.max_seconds = max_seconds
         o.collect_levels = int(collect_levels)
         o.frontier_host_capacity = frontier_host_capacity
+        o.checkpoint_path = checkpoint_path.encode() if checkpoint_path else None
+        o.recover_path = recover_path.encode() if recover_path else None
+        o.checkpoint_seconds = checkpoint_seconds
         return o
 
     @staticmethod
@@ -488,7 +497,7 @@ class ModelChecker:
         acts = (C.c_uint8 * cap)()
         rc = self._lib.vsr_bfs(self._h, C.byref(o), C.byref(st), tr, acts, cap)
         if rc == 153:
-            raise VsrError(rc, "no usable CUDA device / CUDA failure: the BFS has no CPU fallback")
+            raise VsrError(rc, "no usable CUDA device / CUDA failure (the BFS has no CPU fallback), or a checkpoint file could not be read / written")
         raw = bytes(tr)
         sb = self.state_bytes
         trace = [(ACTION_NAMES[acts[i]], raw[i * sb:(i + 1) * sb]) for i in range(int(st.trace_len))]

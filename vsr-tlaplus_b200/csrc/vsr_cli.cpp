@@ -9,6 +9,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
+#include <sys/types.h>
 
 #include <string>
 #include <vector>
@@ -22,8 +24,12 @@ static void usage() {
             "  -depth N             stop after BFS depth N\n"
             "  -dumpTrace tlc FILE  write a counterexample in TLC's `dumpTrace tlc` format\n"
             "  -fp N                fingerprint polynomial index; only 0 (TLC's Polys[0]) is available\n"
-            "  -workers N           accepted for compatibility; the BFS runs on the GPU (likewise -metadir, -checkpoint, -coverage,\n"
-            "                       -fpmem, -fpbits, -cleanup, -nowarning, -tool, ...); -recover and -dfid are refused\n"
+            "  -checkpoint MIN      write a checkpoint at the first level boundary after MIN minutes since the last one (0 = after every\n"
+            "                       level) to <metadir>/vsr.ckpt; a run stopped by -depth also leaves one\n"
+            "  -metadir DIR         where checkpoints go (default: states/, as in TLC)\n"
+            "  -recover DIR         continue from the checkpoint in DIR (or from that file) instead of Init\n"
+            "  -workers N           accepted for compatibility; the BFS runs on the GPU (likewise -coverage, -fpmem, -fpbits, -cleanup,\n"
+            "                       -nowarning, -tool, ...); -dfid is refused\n"
             "  -gpu N               CUDA device ordinal (default 0; with -gpus: the first of N consecutive devices)\n"
             "  -gpus N              shard the state space over N = 1, 2, 4 or 8 GPUs of this node (by fingerprint; the kernel stores\n"
             "                       a successor owned by another GPU straight into that GPU's inbox over NVLink)\n"
@@ -38,6 +44,8 @@ static void usage() {
 int main(int argc, char** argv) {
     const char *cfg = nullptr, *tla = nullptr, *dump = nullptr;
     bool simulate = false, deadlock_flag = false;
+    std::string metadir = "states", ckpt_file, recover_file;
+    double ckpt_minutes = -1;
     int gpus = 1;
     unsigned long long inbox_records = 0, part_states = 0;
     unsigned long long sim_walks = 1ull << 22, sim_seed = 1;
@@ -61,12 +69,15 @@ int main(int argc, char** argv) {
             i += 2;
         } else if (a == "-fp" && i + 1 < argc) {
             if (atoi(argv[++i]) != 0) { fprintf(stderr, "Error: only -fp 0 is available\n"); return 255; }
-        } else if ((a == "-workers" || a == "-metadir" || a == "-checkpoint" || a == "-coverage" || a == "-userFile" || a == "-fpmem" ||
+        } else if (a == "-checkpoint" && i + 1 < argc) ckpt_minutes = atof(argv[++i]);
+        else if (a == "-metadir" && i + 1 < argc) metadir = argv[++i];
+        else if (a == "-recover" && i + 1 < argc) recover_file = argv[++i];
+        else if ((a == "-workers" || a == "-coverage" || a == "-userFile" || a == "-fpmem" ||
                     a == "-fpbits" || a == "-maxSetSize" || a == "-lncheck") && i + 1 < argc) {
             i++; /* TLC tuning / housekeeping flags that have no counterpart here: accepted so existing command lines keep working */
         } else if (a == "-cleanup" || a == "-nowarning" || a == "-tool" || a == "-terse" || a == "-gzip" || a == "-debug") {
-        } else if (a == "-recover" || a == "-dfid" || a == "-generateSpecTE" || a == "-continue-from") {
-            fprintf(stderr, "Error: %s is not available (no checkpoints, no depth-first iterative deepening, no trace-expression specs)\n", a.c_str());
+        } else if (a == "-dfid" || a == "-generateSpecTE" || a == "-continue-from") {
+            fprintf(stderr, "Error: %s is not available (no depth-first iterative deepening, no trace-expression specs)\n", a.c_str());
             return 255;
         } else if (a == "-gpu" && i + 1 < argc) o.device = atoi(argv[++i]);
         else if (a == "-table" && i + 1 < argc) o.table_capacity = strtoull(argv[++i], 0, 10);
@@ -82,6 +93,17 @@ int main(int argc, char** argv) {
         else { fprintf(stderr, "Error: unrecognized option %s\n", a.c_str()); usage(); return 255; }
     }
     if (!cfg) { usage(); return 255; }
+    if (ckpt_minutes >= 0) {
+        mkdir(metadir.c_str(), 0777); /* may exist */
+        ckpt_file = metadir + "/vsr.ckpt";
+        o.checkpoint_path = ckpt_file.c_str();
+        o.checkpoint_seconds = ckpt_minutes * 60.0;
+    }
+    if (!recover_file.empty()) {
+        struct stat sb;
+        if (stat(recover_file.c_str(), &sb) == 0 && S_ISDIR(sb.st_mode)) recover_file += "/vsr.ckpt";
+        o.recover_path = recover_file.c_str();
+    }
     char err[1024];
     VsrModel* m = nullptr;
     int rc = vsr_load(cfg, tla, &m, err, sizeof err);

@@ -191,7 +191,7 @@ int vsr_engine_seed_init(VsrEngine* e) {
     ops->init((uint32_t*)rec.data());
     uint64_t fp = ops->fingerprint((const uint32_t*)rec.data(), e->m->run.use_view);
     if (fp == 0) fp = 1;
-    const int owner = e->world > 1 ? (int)(fp >> e->owner_shift) : e->rank;
+    const int owner = e->world > 1 ? owner_of(fp, e->owner_shift) : e->rank;
     e->level = 0;
     e->n_cur = 0;
     e->cur_base = 0;
@@ -446,7 +446,7 @@ int vsr_engine_lookup(VsrEngine* e, const void* state, int* level_out, int* owne
     const ModelOps* ops = e->m->ops;
     uint64_t fp = ops->fingerprint((const uint32_t*)state, e->m->run.use_view);
     if (fp == 0) fp = 1;
-    const int owner = e->world > 1 ? (int)(fp >> e->owner_shift) : e->rank;
+    const int owner = e->world > 1 ? owner_of(fp, e->owner_shift) : e->rank;
     if (owner_out) *owner_out = owner;
     *level_out = 0;
     if (owner != e->rank) return 0;
@@ -518,12 +518,19 @@ int vsr_bfs(const VsrModel* m, const VsrRunOpts* opts, VsrStats* stats, void* tr
         return rc;
     }
     const double t_setup = now_s() - t0;
-    rc = vsr_engine_seed_init(e);
     VsrLevelInfo li;
-    if (!rc) rc = vsr_engine_finish_level(e, &li);
+    memset(&li, 0, sizeof li);
     int result = 0;
-    bool complete = false;
+    bool complete = false, bounded = false;
     uint64_t bad_id = ~0ull;
+    if (opts->recover_path) { /* TLC -recover: continue from a checkpoint instead of Init */
+        rc = vsr_engine_recover(e, opts->recover_path, nullptr);
+        if (!rc && e->st.violation_level) { result = VSR_RC_VIOLATION; bad_id = e->st.violation_id; } /* found before the checkpoint, run continued past it */
+    } else {
+        rc = vsr_engine_seed_init(e);
+        if (!rc) rc = vsr_engine_finish_level(e, &li);
+    }
+    double last_ckpt = now_s();
     while (!rc) {
         if (li.error_code) { result = VSR_RC_ERROR; break; }
         if (li.overflow) { result = VSR_RC_TOO_LARGE; break; }
@@ -531,10 +538,16 @@ int vsr_bfs(const VsrModel* m, const VsrRunOpts* opts, VsrStats* stats, void* tr
         if (li.violation && !result) { result = VSR_RC_VIOLATION; bad_id = li.violation_id; }
         if (li.deadlock) { result = VSR_RC_DEADLOCK; bad_id = li.deadlock_id; break; }
         if (e->n_cur == 0) { complete = true; break; }
-        if (opts->max_depth && e->level >= opts->max_depth) break;
-        if (opts->max_states && e->st.distinct >= opts->max_states) break;
-        if (opts->max_seconds > 0 && now_s() - t0 >= opts->max_seconds) break;
+        if (opts->max_depth && e->level >= opts->max_depth) { bounded = true; break; }
+        if (opts->max_states && e->st.distinct >= opts->max_states) { bounded = true; break; }
+        if (opts->max_seconds > 0 && now_s() - t0 >= opts->max_seconds) { bounded = true; break; }
         if (e->level >= 254) { result = VSR_RC_TOO_LARGE; break; } /* 8-bit level tag in the seen-set */
+        if (opts->checkpoint_path && now_s() - last_ckpt >= opts->checkpoint_seconds) { /* TLC -checkpoint: at a level boundary */
+            rc = vsr_engine_checkpoint(e, opts->checkpoint_path, nullptr);
+            if (rc) break;
+            last_ckpt = now_s();
+            if (opts->verbose) fprintf(stderr, "Checkpointing of run %s completed (depth %d, %llu distinct states).\n", opts->checkpoint_path, e->level, (unsigned long long)e->st.distinct);
+        }
         rc = vsr_engine_expand(e);
         if (rc) break;
         rc = vsr_engine_finish_level(e, &li);
@@ -542,6 +555,8 @@ int vsr_bfs(const VsrModel* m, const VsrRunOpts* opts, VsrStats* stats, void* tr
             fprintf(stderr, "depth %3d: %12llu new  %12llu generated  %8.3f ms\n", e->level, (unsigned long long)li.new_states,
                     (unsigned long long)li.generated, li.ms);
     }
+    /* a run that stops on a bound (-depth, max_states, max_seconds) leaves a checkpoint to continue from */
+    if (!rc && bounded && opts->checkpoint_path) rc = vsr_engine_checkpoint(e, opts->checkpoint_path, nullptr);
     if (rc) result = rc;
     VsrStats s = e->st;
     s.rc = result;

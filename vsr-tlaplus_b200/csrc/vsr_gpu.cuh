@@ -68,6 +68,17 @@ struct RecHdr {
 };
 constexpr int MAX_WORLD = 8;
 
+/* Owner rank of a fingerprint (world a power of two; shift = 64 - log2(world), 64 when world = 1): the high bits of the
+   fingerprint TIMES AN ODD CONSTANT, not of the fingerprint itself.  FP64 is linear over GF(2): a successor differs from its
+   parent in a handful of bits d, so fp(successor) = fp(parent) ^ A*d, and with plain high bits the destination of a rank's
+   successors would be owner(parent) ^ (a few constants) — measured on the shipped VSR.cfg with 8 ranks: some (sender, owner)
+   pairs carry 10x the records of others (24.5 k vs 2.4 k of 104 k), which overflowed inbox segments sized for the average and
+   loads NVLink unevenly.  The carry chains of an integer multiplication are not linear: the same count is 12.8 - 13.3 k for
+   every pair.  A different constant than table_home's, so that the bucket inside a shard stays uniform. */
+__host__ __device__ __forceinline__ int owner_of(uint64_t fp, int shift) {
+    return shift >= 64 ? 0 : (int)((fp * 0xD6E8FEB86659FD93ULL) >> shift);
+}
+
 struct ExpandParams {
     const uint32_t* in;          /* current frontier, n_in states of L::NW words */
     unsigned long long n_in;
@@ -92,7 +103,7 @@ struct ExpandParams {
     RunCfg run;
     int level;                   /* depth of the states being GENERATED (Init = 1) */
     int check_deadlock;
-    int rank, world, owner_shift;/* owner(fp) = fp >> owner_shift (world a power of two; 64 when world = 1) */
+    int rank, world, owner_shift;/* owner(fp) = owner_of(fp, owner_shift) (world a power of two; shift 64 when world = 1) */
     /* world > 1.  push[d] = where THIS rank's records for rank d go: its segment of rank d's inbox, in rank d's memory,
        mapped here over NVLink (CUDA IPC / peer access) — the expand kernel stores them there itself — or a local staging
        buffer when the host moves them with a collective.  Slots are taken from the local counters ctr->send_count[d]. */
@@ -503,7 +514,7 @@ template <class L, bool MULTI> struct Expander {
             } else if (mult > 0) {
                 fp = fp64_view8<L>(B.fp_tab, v, P.run.use_view != 0);
                 if (fp == 0) fp = 1;
-                const int owner = P.world > 1 ? (int)(fp >> P.owner_shift) : P.rank;
+                const int owner = MULTI ? owner_of(fp, P.owner_shift) : P.rank;
                 trec = make_trec(make_gid(P.rank, P.in_base + B.round_first + si), (uint32_t)cand);
                 if (owner == P.rank) {
                     /* start the seen-set probe now; the check hash, aux key and tags are computed under its latency */

@@ -47,7 +47,7 @@ struct StepMsg {
 struct LevelMsg {
     uint64_t new_states, generated, ties, collisions, frontier, viol_id, dead_id, sent, received;
     double ms, ms_insert;
-    int32_t violation, deadlock, error_code, overflow, late, failed;
+    int32_t violation, deadlock, error_code, overflow, late, failed, ckpt, _pad;
 };
 static_assert(sizeof(LevelMsg) <= VSR_GROUP_MSG_BYTES, "all-gather slot");
 
@@ -194,16 +194,32 @@ int vsr_bfs_sharded(VsrEngine* e, const VsrRunOpts* opts, uint64_t part_states, 
        fan-out is measured, not assumed (2.7 per state on the shipped VSR.cfg, 16 with five replicas): each level's steps are
        sized from the previous level's ratio with a factor of two to spare (an overflow is detected, never silent) */
     const bool auto_part = part_states == 0;
-    double fanout = 16.0;
+    double fanout = 16.0, seg_ratio = 0;
     uint64_t prev_frontier_total = 0;
-    int rc = vsr_engine_reset(e);
-    if (!rc) rc = vsr_engine_seed_init(e);
     VsrStats tot;
     memset(&tot, 0, sizeof tot);
     int result = 0, level = 0;
-    bool complete = false;
+    bool complete = false, bounded = false;
     uint64_t bad_gid = ~0ull;
     double kernel_ms = 0, insert_ms = 0;
+    /* checkpoints: every rank writes / reads <path>.rank<r> at the same level boundary (rank 0's clock decides when) */
+    const std::string ckpt_path = opts->checkpoint_path ? std::string(opts->checkpoint_path) + ".rank" + std::to_string(me) : std::string();
+    double last_ckpt = now_s();
+    bool resumed = false;
+    int rc;
+    if (opts->recover_path) {
+        rc = vsr_engine_recover(e, (std::string(opts->recover_path) + ".rank" + std::to_string(me)).c_str(), &tot);
+        if (!rc) {
+            resumed = true;
+            level = e->level - 1; /* the loop's first pass stands at the checkpoint's level boundary without finishing a level */
+            kernel_ms = tot.seconds_kernels * 1e3;
+            insert_ms = tot.seconds_insert * 1e3;
+            if (tot.violation_level) { result = VSR_RC_VIOLATION; bad_gid = tot.violation_id; }
+        }
+    } else {
+        rc = vsr_engine_reset(e);
+        if (!rc) rc = vsr_engine_seed_init(e);
+    }
     auto fail_all = [&](int code) { /* tell the others (they are, or will be, in a barrier) and leave */
         if (g) vsr_group_abort(g);
         return code;
@@ -213,7 +229,8 @@ int vsr_bfs_sharded(VsrEngine* e, const VsrRunOpts* opts, uint64_t part_states, 
     int step_rc = 0; /* a failure inside the level's steps travels to everybody in the level's all-gather */
     for (;;) {
         VsrLevelInfo li;
-        rc = vsr_engine_finish_level(e, &li);
+        memset(&li, 0, sizeof li);
+        if (!resumed) rc = vsr_engine_finish_level(e, &li);
         level++;
         LevelMsg mine;
         memset(&mine, 0, sizeof mine);
@@ -225,6 +242,7 @@ int vsr_bfs_sharded(VsrEngine* e, const VsrRunOpts* opts, uint64_t part_states, 
         mine.dead_id = li.deadlock ? make_gid(me, li.deadlock_id) : ~0ull;
         mine.ms = li.ms; mine.ms_insert = li.ms_insert;
         mine.late = opts->max_seconds > 0 && now_s() - t0 >= opts->max_seconds;
+        mine.ckpt = !ckpt_path.empty() && now_s() - last_ckpt >= opts->checkpoint_seconds;
         if (W > 1) {
             if (vsr_group_allgather(g, &mine, sizeof mine, all.data())) return set_error(e, "%s", g->last_error);
         } else all[0] = mine;
@@ -247,7 +265,9 @@ int vsr_bfs_sharded(VsrEngine* e, const VsrRunOpts* opts, uint64_t part_states, 
         insert_ms += msi;
         tot.generated += n_gen;
         tot.distinct += n_new;
-        if (level >= 2 && level - 2 < VSR_MAX_LEVELS) {
+        if (resumed) { /* the totals, level tables and verdicts up to this boundary came with the checkpoint */
+            resumed = false;
+        } else if (level >= 2 && level - 2 < VSR_MAX_LEVELS) {
             tot.level_generated[level - 2] = n_gen;
             tot.level_ms[level - 2] = ms; /* slowest rank */
             tot.levels_expanded = level - 1;
@@ -269,29 +289,43 @@ int vsr_bfs_sharded(VsrEngine* e, const VsrRunOpts* opts, uint64_t part_states, 
         }
         if (dead) { result = VSR_RC_DEADLOCK; bad_gid = dmin; break; }
         if (max_frontier == 0) { complete = true; break; }
-        if (opts->max_depth && level >= opts->max_depth) break;
-        if (opts->max_states && tot.distinct >= opts->max_states) break;
-        if (all[0].late) break; /* rank 0's clock decides for everybody */
+        if (opts->max_depth && level >= opts->max_depth) { bounded = true; break; }
+        if (opts->max_states && tot.distinct >= opts->max_states) { bounded = true; break; }
+        if (all[0].late) { bounded = true; break; } /* rank 0's clock decides for everybody */
         if (level >= 254) { result = VSR_RC_TOO_LARGE; break; } /* 8-bit level tag in the seen-set */
+        if (all[0].ckpt) { /* TLC -checkpoint: nothing is in flight at a level boundary, every rank saves its shard */
+            tot.seconds_kernels = kernel_ms * 1e-3;
+            tot.seconds_insert = insert_ms * 1e-3;
+            step_rc = vsr_engine_checkpoint(e, ckpt_path.c_str(), &tot); /* a failure travels to everybody in the next all-gather */
+            last_ckpt = now_s();
+            if (opts->verbose && me == 0 && !step_rc)
+                fprintf(stderr, "Checkpointing of run %s.rank* completed (depth %d, %llu distinct states).\n", opts->checkpoint_path, level, (unsigned long long)tot.distinct);
+        }
         /* ---- the next level, in steps: step k expands part k and pushes into inbox half k & 1, and drains what the
            peers pushed here in step k - 1; one more launch drains the last part's records */
         if (auto_part) {
             if (prev_frontier_total && level >= 4) fanout = std::max(4.0, 2.0 * (double)n_gen / (double)prev_frontier_total);
-            part_states = e->inbox_cap ? std::max<uint64_t>(1024, (uint64_t)((double)e->inbox_cap * W / fanout)) : ~0ull;
+            /* records per expanded state into ONE (sender, owner) segment: twice the average, or twice the fullest segment
+               the last level's steps measured — whichever is larger (owner_of spreads the owners evenly, but the inbox must
+               hold whatever distribution a model produces) */
+            double per_state = fanout / W;
+            if (seg_ratio > 0) per_state = std::max(per_state, 2.0 * seg_ratio);
+            part_states = e->inbox_cap ? std::max<uint64_t>(1024, (uint64_t)((double)e->inbox_cap / per_state)) : ~0ull;
         }
         prev_frontier_total = 0;
         for (int r = 0; r < W; r++) prev_frontier_total += all[r].frontier;
-        const uint64_t nparts = W > 1 ? std::max<uint64_t>(1, (max_frontier + part_states - 1) / part_states) : 1;
         uint32_t drain_counts[MAX_WORLD] = {0};
         bool have_drain = false;
         StepMsg sm, sms[MAX_WORLD];
-        for (uint64_t k = 0; k <= nparts && !step_rc; k++) {
-            if (k == nparts && (W == 1 || !have_drain)) break;
+        double level_ratio = 0;
+        uint64_t first = 0;
+        for (uint64_t k = 0; !step_rc; k++) {
+            const bool expanding = first < max_frontier; /* some rank still has frontier states from `first` on */
+            if (!expanding && (W == 1 || !have_drain)) break;
             memset(&sm, 0, sizeof sm);
-            const uint64_t first = k * part_states;
-            const uint64_t count = (k < nparts && first < e->n_cur) ? std::min(part_states, e->n_cur - first) : 0;
+            const uint64_t count = (expanding && first < e->n_cur) ? std::min(part_states, e->n_cur - first) : 0;
             sm.failed = vsr_engine_step(e, first, count, (int)(k & 1), have_drain ? drain_counts : nullptr, sm.sent);
-            if (W == 1 || k == nparts) { /* the last launch only drains: nothing was pushed, the level's all-gather follows */
+            if (W == 1 || !expanding) { /* the last launch only drains: nothing was pushed, the level's all-gather follows */
                 step_rc = sm.failed;
                 break;
             }
@@ -302,11 +336,40 @@ int vsr_bfs_sharded(VsrEngine* e, const VsrRunOpts* opts, uint64_t part_states, 
                 drain_counts[r] = r == me ? 0 : sms[r].sent[me];
                 have_drain |= drain_counts[r] != 0;
             }
+            /* what this step really put into the fullest segment, per expanded state (every rank sees the whole matrix and
+               every rank's frontier size, so all take the same decision); the next step is sized from it */
+            uint64_t next_part = part_states;
+            if (auto_part) {
+                for (int sr = 0; sr < W; sr++) {
+                    const uint64_t cnt = all[sr].frontier > first ? std::min(part_states, all[sr].frontier - first) : 0;
+                    if (cnt < 4096) continue;
+                    for (int d = 0; d < W; d++)
+                        if (d != sr) level_ratio = std::max(level_ratio, (double)sms[sr].sent[d] / (double)cnt);
+                }
+                if (level_ratio > 0) {
+                    const double per_state = std::max(fanout / W, 2.0 * level_ratio);
+                    next_part = std::max<uint64_t>(1024, (uint64_t)((double)e->inbox_cap / per_state));
+                }
+            }
+            first = part_states >= max_frontier - first ? max_frontier : first + part_states;
+            part_states = next_part;
         }
+        if (level_ratio > 0) seg_ratio = level_ratio;
     }
     if (rc) {
         fail_all(rc);
         return rc;
+    }
+    if (bounded && !ckpt_path.empty()) { /* a run that stops on a bound leaves a checkpoint to continue from */
+        tot.seconds_kernels = kernel_ms * 1e-3;
+        tot.seconds_insert = insert_ms * 1e-3;
+        int crc = vsr_engine_checkpoint(e, ckpt_path.c_str(), &tot), crcs[MAX_WORLD];
+        if (W > 1) {
+            if (vsr_group_allgather(g, &crc, sizeof crc, crcs)) return set_error(e, "%s", g->last_error);
+            for (int r = 0; r < W; r++)
+                if (crcs[r] && !crc) crc = crcs[r];
+        }
+        if (crc) return crc;
     }
     tot.rc = result;
     tot.complete = complete ? 1 : 0;
