@@ -36,8 +36,13 @@ EXPECT = dict(distinct=1173992337, generated=3129587684, depth=47, violation_lev
 # a configuration BOTH arms finish: (R=3, V=2, L=1) WITHOUT SYMMETRY, complete = 697,364 distinct states, depth 30 - totals pinned to
 # the spec's text (tests/golden/spec_text_results.json) - the same-config comparison beside the bounded cfg2 sample of the CPU arm
 SMALL = dict(R=3, V=2, L=1, symmetry=0, distinct=697364, generated=1831657, depth=30)
-# BASELINE configs[2]/[4]: README constants to the first AcknowledgedWriteNotLost violation (needs >= 4 GPUs of memory)
-CFG3 = dict(R=3, V=3, L=3, violation_level=24, distinct=3166753191, table_total=1 << 33, frontier_total=1_600_000_000)
+# BASELINE configs[2]/[4]: README constants to the first AcknowledgedWriteNotLost violation, at every GPU count
+# Sizes per GPU count (level 24 alone is 1.345e9 states of 64 B; 3.17e9 seen-set entries + trace records): one GPU holds the seen-set,
+# the trace and 2 x 560 M frontier states in HBM and lets each frontier buffer continue with 850 M states in pinned host memory (spill)
+CFG3 = dict(R=3, V=3, L=3, violation_level=24, distinct=3166753191,
+            table_total={1: 4_000_000_000, 2: 4_400_000_000, 4: 1 << 33, 8: 1 << 33},
+            frontier_total={1: 560_000_000, 2: 1_500_000_000, 4: 1_600_000_000, 8: 1_600_000_000},
+            frontier_host={1: 850_000_000, 2: 0, 4: 0, 8: 0})
 
 
 def peaks():
@@ -239,11 +244,12 @@ def cfg3_first_violation(pkg, vdist, torch, tdist, group, rank, world, local, de
     sharded over the job's GPUs, to the first AcknowledgedWriteNotLost violation; the published trace's states must be in
     the explored set at depths 1..24 and the checker's own counterexample must be a behaviour of Next ending in the violation."""
     mc = pkg.ModelChecker.from_constants(CFG3["R"], CFG3["V"], CFG3["L"])
-    table_cap = CFG3["table_total"] // world
-    frontier_cap = CFG3["frontier_total"] // world
+    table_cap = CFG3["table_total"][world] // world
+    frontier_cap = CFG3["frontier_total"][world] // world
     barrier()
     t0 = time.time()
-    eng = vdist.GpuEngine(mc, rank, world, device=local, table_capacity=table_cap, frontier_capacity=frontier_cap, keep_trace=True, group=group)
+    eng = vdist.GpuEngine(mc, rank, world, device=local, table_capacity=table_cap, frontier_capacity=frontier_cap, keep_trace=True, group=group,
+                          frontier_host_capacity=CFG3["frontier_host"][world])
     t1 = time.time()
     res = eng.run(stop_on_violation=True, want_trace=True)
     barrier()
@@ -256,7 +262,7 @@ def cfg3_first_violation(pkg, vdist, torch, tdist, group, rank, world, local, de
         steps_ok = bool(trace) and all(trace[i + 1][1] in [t for t, _, _ in mc_lit.successors(trace[i][1])] for i in range(len(trace) - 1))
         viol_ok = bool(trace) and mc_lit.invariant(trace[-1][1]) != 0 and all(mc_lit.invariant(s) == 0 for _, s in trace[:-1])
         out = {"workload": "VSR.tla ReplicaCount=3 Values={v1,v2,v3} StartViewOnTimerLimit=3 (README.md:13-18) to the first AcknowledgedWriteNotLost violation",
-               "n_gpus": world, "rc": res.rc, "violation_depth": res.violation_level, "distinct_states": res.distinct, "states_generated": res.generated,
+               "n_gpus": world, "frontier_states_in_host_memory_per_buffer": CFG3["frontier_host"][world], "rc": res.rc, "violation_depth": res.violation_level, "distinct_states": res.distinct, "states_generated": res.generated,
                "seconds_bfs": t2 - t1, "seconds_setup": t1 - t0, "kernel_seconds": res.kernel_ms_max / 1e3, "states_per_s": res.distinct / (t2 - t1),
                "golden_state_depths": gold, "golden_state_depths_ok": gold == list(range(1, 25)),
                "counterexample_len": len(trace), "counterexample_actions": [a for a, _ in trace],
@@ -275,7 +281,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
-    ap.add_argument("--no-cfg3", action="store_true", help="N >= 4: skip the README-constants first-violation block")
+    ap.add_argument("--no-cfg3", action="store_true", help="skip the README-constants first-violation block (BASELINE configs[2]/[4])")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the end-to-end legs")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "staged"],
                     help="N > 1: p2p = the kernel stores remote successors into the owner's inbox over NVLink, C++ level loop (default); "
@@ -417,7 +423,8 @@ def main():
     e2e_s = sorted(e2e_runs)[1] if e2e_runs else None
 
     cfg3 = None
-    if world >= 4 and not args.no_cfg3 and not staged:
+    if not args.no_cfg3 and not staged:
+        torch.cuda.empty_cache()
         try:
             cfg3 = cfg3_first_violation(pkg, vdist, torch, tdist, group, rank, world, local, dev, barrier)
         except pkg.VsrError as ex:
