@@ -402,7 +402,7 @@ def main():
     # e2e: the public one-call API with host buffers in and out: config text -> parse -> allocate (seen-set, frontiers, inboxes)
     # -> BFS -> stats and counterexample back in host memory -> teardown.  Allocating and clearing tens of GB varies with the
     # box's allocator state, so three runs, median reported, all three in the JSON.
-    e2e_runs, e2e_states, h2d, d2h = [], 0, 0, 0
+    e2e_runs, e2e_states, h2d, d2h, e2e_parts = [], 0, 0, 0, None
     for _ in range(0 if (args.no_e2e or staged) else 3):
         barrier()
         te = time.time()
@@ -410,11 +410,13 @@ def main():
             r2 = pkg.ModelChecker.from_cfg_text(cfg).check(stop_on_violation=False, table_capacity=table_cap, frontier_capacity=frontier_cap)
             e2e_states, h2d, d2h = r2.distinct, r2.bytes_h2d + len(cfg), r2.bytes_d2h + C.sizeof(pkg.checker.VsrStats)
             ok = ok and r2.distinct == EXPECT["distinct"] and r2.rc == 12 and len(r2.trace) == EXPECT["violation_level"]
+            e2e_parts = {"setup": r2.seconds_setup, "bfs_and_trace": r2.seconds_total - r2.seconds_setup}
         else:
             mc2 = pkg.ModelChecker.from_cfg_text(cfg)
             r2 = vdist.check_sharded(mc2, group, device=local, table_capacity=table_cap, frontier_capacity=frontier_cap, stop_on_violation=False)
             e2e_states, h2d, d2h = r2.distinct, r2.bytes_h2d + len(cfg), r2.bytes_d2h + C.sizeof(pkg.checker.VsrStats)
             ok = ok and r2.distinct == EXPECT["distinct"] and r2.rc == 12 and (rank != 0 or len(r2.trace) == EXPECT["violation_level"])
+            e2e_parts = r2.call_seconds
         barrier()
         t = torch.tensor([time.time() - te], dtype=torch.float64, device=dev)
         if world > 1:
@@ -479,6 +481,8 @@ def main():
                          "kernel": "expand_kernel<Layout<3,2,3>> (per-GPU states x B_alg / sum of per-level kernel time, max over ranks)"},
             "e2e": ({"value": e2e_states / e2e_s, "unit": "states/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                      "seconds": e2e_s, "seconds_all_runs": e2e_runs,
+                     # rank 0's wall clock of the LAST run by part: where the call's time goes beside the BFS itself
+                     "seconds_by_part_rank0_last_run": e2e_parts,
                      "api": "ModelChecker.from_cfg_text(cfg).check()" if world == 1 else "dist.check_sharded(ModelChecker.from_cfg_text(cfg), group) on every rank"}
                     if e2e_s else None),
             "probe_roofline": probe,

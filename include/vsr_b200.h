@@ -85,6 +85,9 @@ uint64_t vsr_fingerprint(const VsrModel* m, const void* state);          /* FP64
 /* the same fingerprint by its byte-at-a-time definition (vsr_fingerprint and the GPU use the slicing-by-8 form) */
 uint64_t vsr_fingerprint_bytewise(const VsrModel* m, const void* state);
 uint32_t vsr_aux_key(const VsrModel* m, const void* state);
+/* rank (GPU) that owns a fingerprint when the state space is sharded over `world` = 1, 2, 4 or 8 ranks: the high bits of
+ * fingerprint x an odd constant (FP64 is GF(2)-linear: its own high bits would route a rank's successors to a few peers only) */
+int vsr_owner_rank(uint64_t fingerprint, int world);
 int vsr_invariant(const VsrModel* m, const void* state);                 /* 0 = all hold, else mask bit of the violated one; VSR.tla:926-952 */
 int vsr_unpack(const VsrModel* m, const void* state, VsrFlatState* out);
 int vsr_pack(const VsrModel* m, const VsrFlatState* in, void* state_out);

@@ -26,8 +26,8 @@ class HostEngine:
         self.reset()
 
     def owner(self, fp):
-        # the product's rule (csrc/vsr_gpu.cuh owner_of): high bits of the fingerprint times an odd constant
-        return (((fp * 0xD6E8FEB86659FD93) & 0xFFFFFFFFFFFFFFFF) >> self.shift) if self.world > 1 else self.rank
+        # the product's rule (vsr_owner_rank = csrc/vsr_layout.h owner_of): high bits of the fingerprint times an odd constant
+        return int(self.mc._lib.vsr_owner_rank(fp, self.world)) if self.world > 1 else self.rank
 
     def reset(self):
         self.seen = {}          # fp -> (level, auxkey)

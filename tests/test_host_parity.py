@@ -227,3 +227,40 @@ def test_every_action_is_compared_with_the_oracle(pkg, tmp_path, sym):
     cover = dict(zip(pkg.ACTION_NAMES[1:16], out["action_coverage"]))
     assert all(n > 0 for n in cover.values()), cover
     assert cover["SendGetState"] >= 50 and cover["ReceiveGetState"] >= 100 and cover["ReceiveNewState"] >= 10, cover
+
+
+def test_owner_ranks_spread_every_senders_successors_evenly(pkg):
+    """Sharding: FP64 is linear over GF(2), so with the fingerprint's own high bits as the owner a rank's successors
+    would go to `owner(parent) ^ c` for a handful of constants c — on the shipped VSR.cfg with 8 ranks some (sender, owner) pairs
+    carried 10x the records of others and overflowed their inbox segment (the first 8-GPU run).  vsr_owner_rank must give every
+    pair about the same share, and a uniform split of the states themselves."""
+    mc = pkg.ModelChecker.from_constants(3, 2, 2)
+    lib = mc._lib
+    seen, frontier = {mc.init_state()}, [mc.init_state()]
+    for _ in range(10):  # depth 11: 44,840 states
+        nxt = []
+        for s in frontier:
+            for t, _, _ in mc.successors(s):
+                if t not in seen:
+                    seen.add(t)
+                    nxt.append(t)
+        frontier = nxt
+    for world in (2, 4, 8):
+        mat = [[0] * world for _ in range(world)]
+        plain = [[0] * world for _ in range(world)]
+        shift = 64 - (world.bit_length() - 1)
+        for s in frontier:
+            f = mc.fingerprint(s)
+            a = lib.vsr_owner_rank(f, world)
+            for t, _, _ in mc.successors(s):
+                g = mc.fingerprint(t)
+                mat[a][lib.vsr_owner_rank(g, world)] += 1
+                plain[f >> shift][g >> shift] += 1
+        cells = [c for row in mat for c in row]
+        assert max(cells) < 1.25 * min(cells), mat
+        owners = [sum(row) for row in mat]
+        assert max(owners) < 1.1 * min(owners)
+        if world == 8:  # what the rule replaces, for the record: the plain high bits are far from even
+            pc = [c for row in plain for c in row]
+            assert max(pc) > 4 * min(pc)
+    assert lib.vsr_owner_rank(12345, 1) == 0 and lib.vsr_owner_rank(12345, 3) == -1

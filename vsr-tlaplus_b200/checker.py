@@ -141,7 +141,7 @@ class VsrLevelInfo(C.Structure):
 # every symbol include/vsr_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = [
     "vsr_load", "vsr_load_cfg_text", "vsr_model_create", "vsr_model_free", "vsr_model_info", "vsr_init", "vsr_successors", "vsr_enabled_candidates",
-    "vsr_canon", "vsr_fingerprint", "vsr_fingerprint_bytewise", "vsr_aux_key", "vsr_invariant", "vsr_unpack", "vsr_pack", "vsr_state_to_tla",
+    "vsr_canon", "vsr_fingerprint", "vsr_fingerprint_bytewise", "vsr_aux_key", "vsr_owner_rank", "vsr_invariant", "vsr_unpack", "vsr_pack", "vsr_state_to_tla",
     "vsr_flat_to_tla", "vsr_action_name", "vsr_action_location", "vsr_bfs", "vsr_engine_create", "vsr_engine_destroy",
     "vsr_engine_record_bytes", "vsr_engine_seed_init", "vsr_engine_expand", "vsr_engine_expand_part", "vsr_engine_step",
     "vsr_engine_insert_records", "vsr_engine_finish_level", "vsr_engine_frontier_size", "vsr_engine_read_frontier",
@@ -181,6 +181,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.vsr_fingerprint_bytewise.argtypes = [vp, vp]
     lib.vsr_fingerprint_bytewise.restype = u64
     lib.vsr_aux_key.argtypes = [vp, vp]
+    lib.vsr_owner_rank.argtypes = [u64, C.c_int]
     lib.vsr_aux_key.restype = C.c_uint32
     lib.vsr_invariant.argtypes = [vp, vp]
     lib.vsr_unpack.argtypes = [vp, vp, C.POINTER(VsrFlatState)]

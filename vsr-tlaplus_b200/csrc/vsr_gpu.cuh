@@ -68,16 +68,6 @@ struct RecHdr {
 };
 constexpr int MAX_WORLD = 8;
 
-/* Owner rank of a fingerprint (world a power of two; shift = 64 - log2(world), 64 when world = 1): the high bits of the
-   fingerprint TIMES AN ODD CONSTANT, not of the fingerprint itself.  FP64 is linear over GF(2): a successor differs from its
-   parent in a handful of bits d, so fp(successor) = fp(parent) ^ A*d, and with plain high bits the destination of a rank's
-   successors would be owner(parent) ^ (a few constants) — measured on the shipped VSR.cfg with 8 ranks: some (sender, owner)
-   pairs carry 10x the records of others (24.5 k vs 2.4 k of 104 k), which overflowed inbox segments sized for the average and
-   loads NVLink unevenly.  The carry chains of an integer multiplication are not linear: the same count is 12.8 - 13.3 k for
-   every pair.  A different constant than table_home's, so that the bucket inside a shard stays uniform. */
-__host__ __device__ __forceinline__ int owner_of(uint64_t fp, int shift) {
-    return shift >= 64 ? 0 : (int)((fp * 0xD6E8FEB86659FD93ULL) >> shift);
-}
 
 struct ExpandParams {
     const uint32_t* in;          /* current frontier, n_in states of L::NW words */

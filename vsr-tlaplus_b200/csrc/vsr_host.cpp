@@ -859,6 +859,12 @@ int vsr_canon(const VsrModel* m, void* s) { return m->run.symmetry ? m->ops->can
 uint64_t vsr_fingerprint(const VsrModel* m, const void* s) { return m->ops->fingerprint((const uint32_t*)s, m->run.use_view); }
 uint64_t vsr_fingerprint_bytewise(const VsrModel* m, const void* s) { return m->ops->fingerprint_bytewise((const uint32_t*)s, m->run.use_view); }
 uint32_t vsr_aux_key(const VsrModel* m, const void* s) { return m->ops->aux_key((const uint32_t*)s); }
+int vsr_owner_rank(uint64_t fingerprint, int world) {
+    if (world < 1 || world > 8 || (world & (world - 1))) return -1;
+    int lg = 0;
+    while ((1 << lg) < world) lg++;
+    return vsr::owner_of(fingerprint ? fingerprint : 1, 64 - lg);
+}
 int vsr_invariant(const VsrModel* m, const void* s) { return m->ops->invariant(&m->run, (const uint32_t*)s); }
 int vsr_unpack(const VsrModel* m, const void* s, VsrFlatState* out) { return m->ops->unpack((const uint32_t*)s, out); }
 int vsr_pack(const VsrModel* m, const VsrFlatState* in, void* s) { return m->ops->pack(in, (uint32_t*)s, m->run.symmetry); }

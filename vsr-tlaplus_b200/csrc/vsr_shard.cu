@@ -85,13 +85,16 @@ int vsr_engine_detach(VsrEngine* e) {
 }
 
 uint64_t vsr_engine_default_inbox_records(const VsrEngine* e) {
-    /* a step of S frontier states per rank pushes about S * (successor records per state) * (world - 1) / world records,
-       spread over world - 1 peers.  1/8 of the frontier capacity per segment (at most 16 M records) keeps the inbox
-       (2 halves x world segments) at a fraction of the frontier's memory and gives steps of millions of states, so the
-       per-step host round trip (launch, 32-byte read-back, shared-memory all-gather: ~50 us) stays a few per cent */
-    uint64_t cap = e->frontier_cap / 8;
+    /* a step of S frontier states per rank pushes about S * (successor records per state) / world records into each peer
+       segment.  frontier capacity / (2 x world) records per segment, at most 2^25 / world: the inbox (2 halves x world
+       segments) stays a fraction of the frontier's memory, steps are still hundreds of thousands to millions of states (the
+       per-step host round trip — launch, 32-byte read-back, shared-memory all-gather: ~50 us — stays a few per cent), and what
+       every peer has to map over CUDA IPC when the exchange is attached stays small: with 8 ranks mapping 7 inboxes of 2.7 GB
+       (21 GB for the README constants) was most of the one-call API's 0.9 s around an 0.08 s BFS */
+    const uint64_t w = (uint64_t)(e->world > 1 ? e->world : 1);
+    uint64_t cap = e->frontier_cap / (2 * w);
+    if (cap > (1ull << 25) / w) cap = (1ull << 25) / w;
     if (cap < 4096) cap = 4096;
-    if (cap > (1ull << 24)) cap = 1ull << 24;
     return cap;
 }
 

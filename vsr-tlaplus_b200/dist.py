@@ -116,6 +116,9 @@ class ShardedResult:
     bytes_d2h: int = 0
     trace_cands: List[int] = field(default_factory=list)
     trace: List[Tuple[str, bytes]] = field(default_factory=list)
+    # check_sharded only: this rank's wall clock of the one-call API by part (engine creation = allocation + clearing the
+    # seen-set; attach = inbox allocation + CUDA IPC mapping of the peers; bfs; replay of the counterexample; teardown)
+    call_seconds: dict = field(default_factory=dict)
 
 
 class GpuEngine:
@@ -133,7 +136,9 @@ class GpuEngine:
                                  frontier_host_capacity=frontier_host_capacity)
         self._e = C.c_void_p()
         err = C.create_string_buffer(512)
+        t0 = time.time()
         rc = self.lib.vsr_engine_create(mc._h, C.byref(self._opts), rank, world, C.byref(self._e), err, len(err))
+        self.seconds_create = time.time() - t0
         if rc:
             if group is not None:
                 group.abort()
@@ -144,7 +149,9 @@ class GpuEngine:
         if world > 1 and self.exchange == "p2p":
             if group is None:
                 raise ck.VsrError(255, "exchange='p2p' needs a Group")
+            t0 = time.time()
             self._ck(self.lib.vsr_engine_attach_group(self._e, group._g, inbox_records))
+            self.seconds_attach = time.time() - t0
             self.inbox_records = inbox_records or int(self.lib.vsr_engine_default_inbox_records(self._e))
         elif world > 1:
             stage, inbox, cap = C.c_void_p(), C.c_void_p(), C.c_uint64()
@@ -272,13 +279,20 @@ def check_sharded(mc: "ck.ModelChecker", group: Group, device: int = 0, table_ca
     """One call per rank: engine + inbox + BFS + teardown; on a violation rank 0's result carries the literal trace."""
     eng = GpuEngine(mc, group.rank, group.world, device=device, table_capacity=table_capacity, frontier_capacity=frontier_capacity,
                     inbox_records=inbox_records, keep_trace=keep_trace, check_deadlock=check_deadlock, group=group)
+    res = None
     try:
+        t0 = time.time()
         res = eng.run(part_states=part_states, **run_kw)
+        t1 = time.time()
         if res.trace_cands or res.rc in (11, 12):
             res.trace = replay_trace(mc, res.trace_cands)
+        res.call_seconds = {"create": eng.seconds_create, "attach": getattr(eng, "seconds_attach", 0.0), "bfs": t1 - t0, "replay": time.time() - t1}
         return res
     finally:
+        t2 = time.time()
         eng.close()
+        if res is not None:
+            res.call_seconds["teardown"] = time.time() - t2
 
 
 class ShardedBfs:
