@@ -221,6 +221,28 @@ def run_reference(args, rank):
     }))
 
 
+def host_memory_available():
+    """bytes this process may still allocate on the host: MemAvailable, capped by the cgroup's limit (a GPU box is often a slice of a
+    machine: pinning past the slice's limit gets the whole job killed, not an error code)"""
+    avail = None
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                avail = int(ln.split()[1]) * 1024
+    except OSError:
+        pass
+    for mx, cur in (("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory.current"),
+                    ("/sys/fs/cgroup/memory/memory.limit_in_bytes", "/sys/fs/cgroup/memory/memory.usage_in_bytes")):
+        try:
+            m = open(mx).read().strip()
+            if m != "max":
+                left = int(m) - int(open(cur).read().strip())
+                avail = left if avail is None else min(avail, left)
+        except (OSError, ValueError):
+            pass
+    return avail
+
+
 def golden_depths(pkg, mc, eng, torch, tdist, world, dev, rank):
     """BFS depth at which each state of the reference's published 24-state counterexample (tests/golden/
     state_transfer_trace.json, generated from state_transfer_violation_trace.txt) was first seen; 0 = not in the explored set"""
@@ -244,6 +266,12 @@ def cfg3_first_violation(pkg, vdist, torch, tdist, group, rank, world, local, de
     sharded over the job's GPUs, to the first AcknowledgedWriteNotLost violation; the published trace's states must be in
     the explored set at depths 1..24 and the checker's own counterexample must be a behaviour of Next ending in the violation."""
     mc = pkg.ModelChecker.from_constants(CFG3["R"], CFG3["V"], CFG3["L"])
+    pinned = 2 * CFG3["frontier_host"][world] * mc.state_bytes
+    if pinned:
+        avail = host_memory_available()
+        if avail is None or pinned > 0.6 * avail:
+            return {"skipped": "needs %.0f GB of pinned host memory for the frontier spill; %s available to this job"
+                               % (pinned / 1e9, "unknown" if avail is None else "%.0f GB" % (avail / 1e9))}
     table_cap = CFG3["table_total"][world] // world
     frontier_cap = CFG3["frontier_total"][world] // world
     barrier()
@@ -281,7 +309,10 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
-    ap.add_argument("--no-cfg3", action="store_true", help="skip the README-constants first-violation block (BASELINE configs[2]/[4])")
+    ap.add_argument("--no-cfg3", action="store_true", help="N >= 2: skip the README-constants first-violation block (BASELINE configs[2]/[4])")
+    ap.add_argument("--cfg3-one-gpu", action="store_true",
+                    help="N = 1: run that block too: 3.17e9 states on ONE GPU with the frontier spilling into 109 GB of pinned host memory "
+                         "(off by default: a box that is a slice of a machine may not have that much)")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the end-to-end legs")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "staged"],
                     help="N > 1: p2p = the kernel stores remote successors into the owner's inbox over NVLink, C++ level loop (default); "
@@ -425,7 +456,7 @@ def main():
     e2e_s = sorted(e2e_runs)[1] if e2e_runs else None
 
     cfg3 = None
-    if not args.no_cfg3 and not staged:
+    if (world > 1 and not args.no_cfg3 and not staged) or (world == 1 and args.cfg3_one_gpu):
         torch.cuda.empty_cache()
         try:
             cfg3 = cfg3_first_violation(pkg, vdist, torch, tdist, group, rank, world, local, dev, barrier)

@@ -16,14 +16,22 @@ build() { # name, flags
     g++ -O2 -std=c++17 -fPIC $ONLY $2 -c vsr_host.cpp -o $OUT/vsr_host_$1.o   # the host side shares the flags (fingerprints must agree)
     nvcc $ARCH -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -diag-suppress 128 $ONLY $2 -c vsr_gpu.cu -o $OUT/vsr_gpu_$1.o &
     nvcc $ARCH -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -diag-suppress 128 $ONLY $2 -c vsr_shard.cu -o $OUT/vsr_shard_$1.o &
+    nvcc $ARCH -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -diag-suppress 128 $ONLY $2 -c vsr_ckpt.cu -o $OUT/vsr_ckpt_$1.o &
     wait
-    nvcc $ARCH -shared -Xlinker -Bsymbolic -o $OUT/libvsr_b200_$1.so $OUT/vsr_gpu_$1.o $OUT/vsr_shard_$1.o $OUT/vsr_group.o $OUT/vsr_host_$1.o -ldl -lpthread -lrt
-    rm -f $OUT/vsr_gpu_$1.o $OUT/vsr_shard_$1.o $OUT/vsr_host_$1.o
+    nvcc $ARCH -shared -Xlinker -Bsymbolic -o $OUT/libvsr_b200_$1.so $OUT/vsr_gpu_$1.o $OUT/vsr_shard_$1.o $OUT/vsr_ckpt_$1.o $OUT/vsr_group.o $OUT/vsr_host_$1.o -ldl -lpthread -lrt
+    rm -f $OUT/vsr_gpu_$1.o $OUT/vsr_shard_$1.o $OUT/vsr_ckpt_$1.o $OUT/vsr_host_$1.o
     echo "built $OUT/libvsr_b200_$1.so"
 }
 build base ""
+build pushfast "-DVSR_EXP_PUSHFAST"      # pool layout without the per-pair bound test when the round's pairs fit the pool (the usual case)
+build loadfast "-DVSR_EXP_LOADFAST"      # parent load without a division per word
+build warps32 "-DVSR_FORCE_WARPS=32"     # ONE block of 32 warps per SM (1024 parents per round) instead of two of 16: half the end-of-round tail, all warps in the same phase
+build warps32pl "-DVSR_FORCE_WARPS=32 -DVSR_EXP_PUSHFAST -DVSR_EXP_LOADFAST"
+build pl "-DVSR_EXP_PUSHFAST -DVSR_EXP_LOADFAST"
+if [ -n "$VSR_VARIANTS_ALL" ]; then
 build bucket1 "-DVSR_BUCKET=1"           # seen-set probe = one 128-bit load of one entry (round 1); default is the 2-entry sector bucket
 build bucket4 "-DVSR_BUCKET=4"           # 4-entry bucket, two 256-bit loads issued together
+fi
 
 build qps1 "-DVSR_QPS=1"                 # correctness variant (pool overflow path): VSR_B200_LIB=...qps1.so python -m pytest tests/test_gpu_parity.py -k "3-2-2 or deterministic"
 rm -f $OUT/vsr_group.o

@@ -603,7 +603,8 @@ template <class L, bool MULTI> struct Expander {
     static constexpr int MW = moff(NG);       /* mask words per state */
     static constexpr int PW = (NG + 1) / 2;   /* packed 16-bit counters, two groups per word */
     static __host__ __device__ constexpr int max_grp() { int m = 0; for (int g = 0; g < NG; g++) m = O_::grp_size(g) > m ? O_::grp_size(g) : m; return m; }
-    static_assert(max_grp() < 128 && NS <= 512, "pool item = thread (9 bits) | candidate offset in its group (7 bits)");
+    static constexpr int TBITS = NS <= 512 ? 9 : 10; /* pool item = thread (TBITS bits) | candidate offset in its group (the other 16 - TBITS) */
+    static_assert(NS <= (1 << TBITS) && max_grp() < (1 << (16 - TBITS)), "pool item does not fit 16 bits");
     static_assert(max_grp() * NS < 65536, "16-bit packed counters");
 
     template <int G> __device__ __forceinline__ void guards(const RegRow<L::NW>& st, uint32_t* m, uint32_t* pc) {
@@ -615,7 +616,8 @@ template <class L, bool MULTI> struct Expander {
         if constexpr (G + 1 < NG) guards<G + 1>(st, m, pc);
     }
     /* write this lane's pairs of group G (and the following groups) to the pool; pairs that do not fit stay in m */
-    template <int G> __device__ __forceinline__ void push(uint32_t* m, const uint32_t* ex, const uint32_t* wb, int st) {
+    /* FAST: the whole round's pairs fit the pool (the caller has checked): no bound test per pair, nothing left over */
+    template <int G, bool FAST> __device__ __forceinline__ void push(uint32_t* m, const uint32_t* ex, const uint32_t* wb, int st) {
         int pos = st + (int)((wb[G >> 1] >> (16 * (G & 1))) & 0xFFFFu) + (int)((ex[G >> 1] >> (16 * (G & 1))) & 0xFFFFu);
         VSR_UNROLL
         for (int k = 0; k < O_::grp_words(G); k++) {
@@ -623,15 +625,15 @@ template <class L, bool MULTI> struct Expander {
             while (mm) {
                 const int bit = __ffs(mm) - 1;
                 mm &= mm - 1;
-                if (pos < Smem::QCAP) B.pool[pos] = (uint16_t)(tid | ((k * 32 + bit) << 9));
+                if (FAST || pos < Smem::QCAP) B.pool[pos] = (uint16_t)(tid | ((k * 32 + bit) << TBITS));
                 else left |= 1u << bit;
                 pos++;
             }
-            m[moff(G) + k] = left;
+            if (!FAST) m[moff(G) + k] = left;
         }
         if constexpr (G + 1 < NG) {
-            const int nst = st + B.qcount[G] < Smem::QCAP ? st + B.qcount[G] : Smem::QCAP;
-            push<G + 1>(m, ex, wb, nst);
+            const int nst = FAST ? st + B.qcount[G] : (st + B.qcount[G] < Smem::QCAP ? st + B.qcount[G] : Smem::QCAP);
+            push<G + 1, FAST>(m, ex, wb, nst);
         }
     }
     /* pool full (rare): the pairs left in m are applied right here by their own lanes, one group at a time */
@@ -692,7 +694,16 @@ template <class L, bool MULTI> struct Expander {
         for (int g = 0; g < NG; g++) wb[g >> 1] |= (__shfl_sync(0xffffffffu, mybase, g) & 0xFFFFu) << (16 * (g & 1));
         if (P.check_deadlock && have && !anyc) atomicMin(&P.ctr->dead_id, P.in_base + B.round_first + tid);
         __syncthreads(); /* qcount[] final: group g's segment starts at min(sum of the groups before it, QCAP) */
-        push<0>(m, ex, wb, 0);
+#ifdef VSR_EXP_PUSHFAST
+        int all = 0;
+        VSR_UNROLL
+        for (int g = 0; g < NG; g++) all += B.qcount[g];
+        if (all <= Smem::QCAP) { /* block-uniform: the usual case */
+            push<0, true>(m, ex, wb, 0);
+            return;
+        }
+#endif
+        push<0, false>(m, ex, wb, 0);
         uint32_t rest = 0;
         VSR_UNROLL
         for (int i = 0; i < MW; i++) rest |= m[i];
@@ -713,8 +724,8 @@ template <class L, bool MULTI> struct Expander {
         int cand = 0, si = 0;
         if (act) {
             const unsigned item = B.pool[b + lane];
-            si = item & 511;
-            cand = O_::grp_begin(G) + (int)(item >> 9);
+            si = item & ((1 << TBITS) - 1);
+            cand = O_::grp_begin(G) + (int)(item >> TBITS);
         }
         return apply<G>(P, B, S, lane, &B.par[si * (L::NW + 1)], cand, si, act);
     }
@@ -728,7 +739,18 @@ template <class L, bool MULTI> struct Expander {
         /* coalesced load of `count` parent states into padded rows */
         const uint32_t* src = P.in + first * L::NW;
         if (first + count <= P.in_split) {
+#ifdef VSR_EXP_LOADFAST
+            /* word i of the round goes to row i / NW, column i % NW: quotient and remainder carried along instead of divided out */
+            constexpr int QS = NS / L::NW, RS = NS % L::NW;
+            int q = tid / L::NW, r = tid % L::NW;
+            for (int i = tid; i < count * L::NW; i += NS) {
+                B.par[q * (L::NW + 1) + r] = __ldg(src + i);
+                q += QS; r += RS;
+                if (r >= L::NW) { r -= L::NW; q++; }
+            }
+#else
             for (int i = tid; i < count * L::NW; i += NS) B.par[(i / L::NW) * (L::NW + 1) + (i % L::NW)] = __ldg(src + i);
+#endif
         } else { /* (part of) this round's parents are in the host part of the frontier */
             for (int i = tid; i < count * L::NW; i += NS) {
                 const unsigned long long st = first + i / L::NW;
@@ -797,7 +819,7 @@ template <class L, bool MULTI> struct Expander {
     }
 };
 
-template <class L, bool MULTI> __global__ void __launch_bounds__(ExpandCfg<L>::WARPS * 32, 2) expand_kernel(const __grid_constant__ ExpandParams P) {
+template <class L, bool MULTI> __global__ void __launch_bounds__(ExpandCfg<L>::WARPS * 32, ExpandCfg<L>::WARPS > 16 ? 1 : 2) expand_kernel(const __grid_constant__ ExpandParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     typedef typename ExpandCfg<L>::Smem Smem;
     Smem& B = *reinterpret_cast<Smem*>(smem_raw);
