@@ -22,12 +22,10 @@ build() { # name, flags
     rm -f $OUT/vsr_gpu_$1.o $OUT/vsr_shard_$1.o $OUT/vsr_ckpt_$1.o $OUT/vsr_host_$1.o
     echo "built $OUT/libvsr_b200_$1.so"
 }
-build base ""
-build pushfast "-DVSR_EXP_PUSHFAST"      # pool layout without the per-pair bound test when the round's pairs fit the pool (the usual case)
-build loadfast "-DVSR_EXP_LOADFAST"      # parent load without a division per word
-build warps32 "-DVSR_FORCE_WARPS=32"     # ONE block of 32 warps per SM (1024 parents per round) instead of two of 16: half the end-of-round tail, all warps in the same phase
-build warps32pl "-DVSR_FORCE_WARPS=32 -DVSR_EXP_PUSHFAST -DVSR_EXP_LOADFAST"
-build pl "-DVSR_EXP_PUSHFAST -DVSR_EXP_LOADFAST"
+build base ""                            # the default: one block of up to 32 warps per SM, pool fast path
+build warps16 "-DVSR_FORCE_WARPS=16"     # two blocks of 16 warps per SM (the shape until the re-entry session's A/B: +13 % kernel time)
+build invskip "-DVSR_EXP_INVSKIP"        # inline invariant only after the action groups that can falsify it (they rewrite a log / acknowledge a value)
+build nopushfast "-DVSR_EXP_NO_PUSHFAST" # pool layout with the per-pair bound test always (+0.8 %)
 if [ -n "$VSR_VARIANTS_ALL" ]; then
 build bucket1 "-DVSR_BUCKET=1"           # seen-set probe = one 128-bit load of one entry (round 1); default is the 2-entry sector bucket
 build bucket4 "-DVSR_BUCKET=4"           # 4-entry bucket, two 256-bit loads issued together

@@ -275,13 +275,27 @@ template <class L, int WARPS> struct BlockSmemT {
     unsigned long long round_first;
     WarpStage<L> w[WARPS];
 };
-/* warps per block: as many as fit twice per SM (2 x <= 113 KB of shared memory) */
+/* Block shape.  ONE block of up to 32 warps per SM when its shared memory fits (227 KB), else two blocks of 16 / 12 / 8 warps
+   (2 x <= 113 KB).  Measured on the shipped VSR.cfg (profiles/round2_expand_kernel.md section 5): one block of 32 warps — rounds of
+   1024 parents — takes 13 % less kernel time than two blocks of 16 with the same 32 resident warps: the end-of-round tail (the
+   barrier stall of section 4) halves, and all warps of the SM run the same phase, so they share the instruction cache lines of the
+   scan.  The pool item keeps 16 bits: thread (10) | candidate offset in its group (6), which bounds a group at 63 candidates. */
 template <class L> struct ExpandCfg {
+    static constexpr size_t SMEM_ONE = 227 * 1024 - 512, SMEM_TWO = 113 * 1024;
+    static constexpr int max_grp() { int m = 0; for (int g = 0; g < Ops<L>::NGRP; g++) m = Ops<L>::grp_size(g) > m ? Ops<L>::grp_size(g) : m; return m; }
+    template <int W> static constexpr int pick_one() { /* most warps (even) of ONE block per SM; 0: not even 18 fit */
+        if constexpr (W < 18) return 0;
+        else if constexpr (sizeof(BlockSmemT<L, W>) <= SMEM_ONE) return W;
+        else return pick_one<W - 2>();
+    }
+    static constexpr int W2 = sizeof(BlockSmemT<L, 16>) <= SMEM_TWO ? 16 : (sizeof(BlockSmemT<L, 12>) <= SMEM_TWO ? 12 : 8);
+    static constexpr int W1 = max_grp() < 64 ? pick_one<32>() : 0;
 #ifdef VSR_FORCE_WARPS
     static constexpr int WARPS = VSR_FORCE_WARPS; /* tuning experiments only */
 #else
-    static constexpr int WARPS = sizeof(BlockSmemT<L, 16>) <= 113 * 1024 ? 16 : (sizeof(BlockSmemT<L, 12>) <= 113 * 1024 ? 12 : 8);
+    static constexpr int WARPS = W1 >= 2 * W2 - 4 ? W1 : W2; /* one block unless it would cost more than 4 resident warps */
 #endif
+    static constexpr int BLOCKS = WARPS > 16 ? 1 : 2;
     typedef BlockSmemT<L, WARPS> Smem;
 };
 
@@ -431,7 +445,7 @@ template <class L, bool MULTI> struct Expander {
        probes (high half); the caller keeps the running sums in registers (a warp reduction per batch cost 25 shuffles) */
     static __device__ __forceinline__ unsigned long long commit(const ExpandParams& P, WarpStage<L>& S, int lane, const RegRow<L::NW>& v, bool live, uint64_t fp,
                                                                 uint32_t chk, uint32_t auxkey, unsigned long long home, const Probe& first, unsigned long long trec,
-                                                                unsigned mult) {
+                                                                unsigned mult, bool check_inv = true) {
         unsigned gen = 0, probes = 0, coll = 0;
         int sn = S.sn;
         bool isnew = false;
@@ -442,7 +456,7 @@ template <class L, bool MULTI> struct Expander {
             const int r = table_insert_from(P.table, P.table_cap, home, first, fp, meta, probes, coll);
             isnew = r == INS_NEW;
             if (r == INS_FULL) atomicExch(&P.ctr->overflow, 4);
-            if (isnew) bad = O_::invariant(P.run, v);
+            if (isnew && check_inv) bad = O_::invariant(P.run, v);
             if (coll) atomicAdd(&P.ctr->collisions, (unsigned long long)coll); /* never seen so far */
             if (r == INS_TIE) {
                 atomicAdd(&P.ctr->ties, 1ull);
@@ -484,7 +498,7 @@ template <class L, bool MULTI> struct Expander {
 
     /* fingerprint and route one successor per lane: the part of apply that does not depend on the action */
     static __device__ __noinline__ unsigned long long emit(const ExpandParams& P, Smem& B, WarpStage<L>& S, int lane, const Row n, int mult,
-                                                           int cand, int si, bool act) {
+                                                           int cand, int si, bool act, bool check_inv) {
         int send_to = -1;
         uint64_t fp = 0;
         uint32_t chk = 0, auxkey = 0;
@@ -522,7 +536,7 @@ template <class L, bool MULTI> struct Expander {
             __syncwarp(); /* every lane has read its scratch row: that half of the staging area may now carry outgoing records */
             push_records(P, S, lane, v, send_to, fp, trec | ((uint64_t)(unsigned)mult << 56));
         }
-        return commit(P, S, lane, v, live, fp, chk, auxkey, home, first, trec, (unsigned)mult);
+        return commit(P, S, lane, v, live, fp, chk, auxkey, home, first, trec, (unsigned)mult, check_inv);
     }
 
     /* ---- drain: one record received from a peer per lane (world > 1), after this block's share of the frontier.  The
@@ -694,7 +708,7 @@ template <class L, bool MULTI> struct Expander {
         for (int g = 0; g < NG; g++) wb[g >> 1] |= (__shfl_sync(0xffffffffu, mybase, g) & 0xFFFFu) << (16 * (g & 1));
         if (P.check_deadlock && have && !anyc) atomicMin(&P.ctr->dead_id, P.in_base + B.round_first + tid);
         __syncthreads(); /* qcount[] final: group g's segment starts at min(sum of the groups before it, QCAP) */
-#ifdef VSR_EXP_PUSHFAST
+#ifndef VSR_EXP_NO_PUSHFAST
         int all = 0;
         VSR_UNROLL
         for (int g = 0; g < NG; g++) all += B.qcount[g];
@@ -715,7 +729,13 @@ template <class L, bool MULTI> struct Expander {
         const Row n = scratch(S, lane);
         int mult = 0;
         if (act) mult = O_::template step_grp<true, G>(P.run, parent, cand, n);
-        return emit(P, B, S, lane, n, mult, cand, si, act);
+#ifdef VSR_EXP_INVSKIP
+        /* the invariants read the replicas' logs and the acknowledgements only (VSR.tla:933-950): a successor of a state that
+           satisfies them can violate them only through an action that rewrites a log or acknowledges a value (Ops::may_falsify) */
+        return emit(P, B, S, lane, n, mult, cand, si, act, O_::may_falsify(G));
+#else
+        return emit(P, B, S, lane, n, mult, cand, si, act, true);
+#endif
     }
     /* one batch of <= 32 queued pairs of group G, pool[b .. b + k) */
     template <int G> static __device__ __forceinline__ unsigned long long batch(const ExpandParams& P, Smem& B, WarpStage<L>& S, int lane, int b,
@@ -739,18 +759,7 @@ template <class L, bool MULTI> struct Expander {
         /* coalesced load of `count` parent states into padded rows */
         const uint32_t* src = P.in + first * L::NW;
         if (first + count <= P.in_split) {
-#ifdef VSR_EXP_LOADFAST
-            /* word i of the round goes to row i / NW, column i % NW: quotient and remainder carried along instead of divided out */
-            constexpr int QS = NS / L::NW, RS = NS % L::NW;
-            int q = tid / L::NW, r = tid % L::NW;
-            for (int i = tid; i < count * L::NW; i += NS) {
-                B.par[q * (L::NW + 1) + r] = __ldg(src + i);
-                q += QS; r += RS;
-                if (r >= L::NW) { r -= L::NW; q++; }
-            }
-#else
             for (int i = tid; i < count * L::NW; i += NS) B.par[(i / L::NW) * (L::NW + 1) + (i % L::NW)] = __ldg(src + i);
-#endif
         } else { /* (part of) this round's parents are in the host part of the frontier */
             for (int i = tid; i < count * L::NW; i += NS) {
                 const unsigned long long st = first + i / L::NW;
@@ -819,7 +828,7 @@ template <class L, bool MULTI> struct Expander {
     }
 };
 
-template <class L, bool MULTI> __global__ void __launch_bounds__(ExpandCfg<L>::WARPS * 32, ExpandCfg<L>::WARPS > 16 ? 1 : 2) expand_kernel(const __grid_constant__ ExpandParams P) {
+template <class L, bool MULTI> __global__ void __launch_bounds__(ExpandCfg<L>::WARPS * 32, ExpandCfg<L>::BLOCKS) expand_kernel(const __grid_constant__ ExpandParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     typedef typename ExpandCfg<L>::Smem Smem;
     Smem& B = *reinterpret_cast<Smem*>(smem_raw);
