@@ -224,6 +224,26 @@ VSR_UNROLL
         probe_load(table, h, p);
     }
 }
+#if defined(VSR_EXP_CASFIRST) && VSR_BUCKET == 2
+/* experiment (tools/variants.sh casfirst): no probe load — the first access of the home bucket IS the compare-and-swap of its
+   first slot.  A new state whose home slot is free is in after ONE round trip instead of two (load, then CAS), a duplicate
+   sitting in the home slot is recognised from the CAS's return value; only a home slot held by another state costs the second
+   access (the bucket's other slot).  Every access becomes an atomic. */
+__device__ __forceinline__ int table_insert_casfirst(uint64_t* table, unsigned long long cap, unsigned long long h, uint64_t fp, uint64_t meta,
+                                                     unsigned& probes, unsigned& collisions) {
+    Probe p;
+    cas128(table + 2 * h, fp, meta, p.e[0], p.e[1]);
+    if (p.e[0] == 0 && p.e[1] == 0) { probes++; return INS_NEW; }
+    if (p.e[0] == fp && (uint32_t)p.e[1] == (uint32_t)meta) {
+        probes++;
+        const bool same_level = (p.e[1] >> 56) == (meta >> 56);
+        const bool same_aux = ((p.e[1] >> 32) & 0xFFFFFF) == ((meta >> 32) & 0xFFFFFF);
+        return (same_level && !same_aux) ? INS_TIE : INS_DUP;
+    }
+    ld128_cg(table + 2 * (h + 1), p.e[2], p.e[3]);
+    return table_insert_from(table, cap, h, p, fp, meta, probes, collisions);
+}
+#endif
 __device__ __forceinline__ int table_insert(uint64_t* table, unsigned long long cap, uint64_t fp, uint64_t meta,
                                             unsigned& probes, unsigned& collisions) {
     const unsigned long long h = table_home(cap, fp);
@@ -453,7 +473,12 @@ template <class L, bool MULTI> struct Expander {
         if (live) {
             const uint64_t meta = make_meta(P.level, auxkey, chk);
             gen = mult;
+#if defined(VSR_EXP_CASFIRST) && VSR_BUCKET == 2
+            (void)first;
+            const int r = table_insert_casfirst(P.table, P.table_cap, home, fp, meta, probes, coll);
+#else
             const int r = table_insert_from(P.table, P.table_cap, home, first, fp, meta, probes, coll);
+#endif
             isnew = r == INS_NEW;
             if (r == INS_FULL) atomicExch(&P.ctr->overflow, 4);
             if (isnew && check_inv) bad = O_::invariant(P.run, v);
@@ -524,7 +549,9 @@ template <class L, bool MULTI> struct Expander {
                     /* start the seen-set probe now; the check hash, aux key and tags are computed under its latency */
                     live = true;
                     home = table_home(P.table_cap, fp);
+#if !(defined(VSR_EXP_CASFIRST) && VSR_BUCKET == 2)
                     probe_load(P.table, home, first);
+#endif
                     chk = check_hash<L>(v, P.run.use_view != 0);
                     auxkey = O_::aux_key(v);
                 } else {
@@ -577,7 +604,9 @@ template <class L, bool MULTI> struct Expander {
             d.fp = ((uint64_t)h.y << 32) | h.x;
             d.tm = ((uint64_t)h.w << 32) | h.z;
             d.home = table_home(P.table_cap, d.fp);
+#if !(defined(VSR_EXP_CASFIRST) && VSR_BUCKET == 2)
             probe_load(P.table, d.home, d.first);
+#endif
         }
         return d;
     }
