@@ -268,6 +268,7 @@ int vsr_bfs_sharded(VsrEngine* e, const VsrRunOpts* opts, uint64_t part_states, 
         insert_ms += msi;
         tot.generated += n_gen;
         tot.distinct += n_new;
+        const bool boundary_only = resumed; /* first pass after a recovery: stands at the checkpoint's level boundary */
         if (resumed) { /* the totals, level tables and verdicts up to this boundary came with the checkpoint */
             resumed = false;
         } else if (level >= 2 && level - 2 < VSR_MAX_LEVELS) {
@@ -279,7 +280,7 @@ int vsr_bfs_sharded(VsrEngine* e, const VsrRunOpts* opts, uint64_t part_states, 
             tot.level_sizes[level - 1] = n_new;
             tot.num_levels = level;
         }
-        if (opts->verbose && me == 0 && level >= 2)
+        if (opts->verbose && me == 0 && level >= 2 && !boundary_only)
             fprintf(stderr, "depth %3d: %12llu new  %12llu generated  %8.3f ms (slowest of %d GPUs)\n", level, (unsigned long long)n_new, (unsigned long long)n_gen, ms, W);
         if (err) { result = VSR_RC_ERROR; tot.error_code = err; break; }
         if (ovf) { result = VSR_RC_TOO_LARGE; break; }
