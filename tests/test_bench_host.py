@@ -60,3 +60,16 @@ def test_level_reduce_on_one_rank_is_the_identity():
 
     b = vdist.ShardedBfs(_E(), 0, 1)
     assert b._reduce_level([1, 2], [3], [4, 5]) == ([1, 2], [3], [4, 5])
+
+
+def test_one_gpu_readme_block_is_guarded_by_the_hosts_memory():
+    """bench.py pins 109 GB of host memory for the README constants on ONE GPU only when the job may have them (a box that is a
+    slice of a machine kills a job that pins past its cgroup limit instead of returning an error): the guard reads MemAvailable
+    and the cgroup limit, and the sizes of every GPU count are there"""
+    import bench
+    avail = bench.host_memory_available()
+    assert avail is None or 0 < avail < 1 << 50
+    for world in (1, 2, 4, 8):
+        assert bench.CFG3["table_total"][world] // world * 7 // 8 >= bench.CFG3["distinct"] // world  # the seen-set's 7/8 load limit
+        per_gpu = bench.CFG3["frontier_total"][world] // world + bench.CFG3["frontier_host"][world]
+        assert per_gpu * world >= 1_344_894_424  # depth 24 of the README constants (profiles/cfg3_counterexample)
