@@ -6,7 +6,7 @@
  * A checkpoint is taken at a level boundary — every state of depth <= level is in the seen-set, the current frontier holds
  * exactly the states of depth `level`, nothing is in flight between ranks — and is ONE file per rank:
  *
- *   CkptHeader | VsrStats totals | frontier: n_cur packed states | seen-set: n_entries x {fp, meta} | trace: next_base x 8 B
+ *   CkptHeader | VsrStats of this rank | VsrStats totals of the job | frontier: n_cur packed states | seen-set: n_entries x {fp, meta} | trace: next_base x 8 B
  *
  * The seen-set is written as its non-empty entries (compacted on the device into the idle frontier buffer, chunk by chunk)
  * and re-inserted on recovery with the BFS's own insert routine, so the table a run continues with may have another
@@ -15,6 +15,7 @@
 #include <errno.h>
 #include <stdio.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <string>
@@ -197,7 +198,7 @@ int vsr_engine_checkpoint(VsrEngine* e, const char* path, const VsrStats* totals
         e->st.bytes_d2h += h.n_trace * 8;
     }
     e->st.bytes_d2h += e->n_cur * S;
-    if (fflush(out.f) != 0) return io_error(e, "cannot write", tmp.c_str());
+    if (fflush(out.f) != 0 || fsync(fileno(out.f)) != 0) return io_error(e, "cannot write", tmp.c_str()); /* on disk before it replaces the previous one */
     fclose(out.f);
     out.f = nullptr;
     if (rename(tmp.c_str(), path) != 0) return io_error(e, "cannot rename to", path);
